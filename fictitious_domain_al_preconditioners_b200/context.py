@@ -1,0 +1,273 @@
+"""Host-side handle on one ``fdal_ctx`` (see ``include/fdal.h``).
+
+``ALContext`` is a thin, typed wrapper: numpy / scipy in, numpy out.  It does
+no arithmetic itself — every ``apply_*`` / ``solve`` call goes through the C
+ABI into the CUDA library, which must be present (``lib.load()`` raises
+otherwise; there is no CPU fallback).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _binding as b
+
+
+class FdalError(RuntimeError):
+    """Non-zero status from the C ABI.  ``status`` carries the FDAL_ERR_* code."""
+
+    def __init__(self, status: int, message: str):
+        super().__init__(f"fdal status {status}: {message}")
+        self.status = status
+
+
+class NoConvergence(FdalError):
+    """Mirror of dealii::SolverControl::NoConvergence (inner or outer solver)."""
+
+
+@dataclass
+class SolverControl:
+    """deal.II SolverControl / ReductionControl / IterationNumberControl."""
+
+    max_steps: int = 100
+    tol: float = 1e-10
+    reduce: float = 0.0
+    type: int = b.CONTROL_SOLVER
+
+    def c(self) -> b.Control:
+        return b.Control(self.type, self.max_steps, self.tol, self.reduce)
+
+
+def ReductionControl(max_steps=100, tol=1e-10, reduce=1e-2):
+    return SolverControl(max_steps, tol, reduce, b.CONTROL_REDUCTION)
+
+
+def IterationNumberControl(max_steps=100, tol=1e-12):
+    return SolverControl(max_steps, tol, 0.0, b.CONTROL_ITERATION_NUMBER)
+
+
+@dataclass
+class ALConfig:
+    kind: int = b.KIND_LAPLACE
+    restart: int = 30
+    gamma: float = 10.0
+    gamma2: float = 0.0
+    gamma_grad_div: float = 0.0
+    winv_mode: int = b.WINV_DIAG
+    mp_inv_mode: int = b.MPINV_CG_LUMPED
+    aug_explicit: bool = False
+    grad_div_in_operator: bool = False
+    inner_prec: int = b.PREC_AMG
+    device: int = 0
+    use_graphs: bool = True
+    exact_mass_max_its: int = 0
+    outer: SolverControl = field(default_factory=lambda: ReductionControl(1000, 1e-10, 1e-12))
+    inner: SolverControl = field(default_factory=lambda: SolverControl(100, 1e-2))
+    mass: SolverControl = field(default_factory=lambda: SolverControl(100, 1e-6))
+
+    def c(self) -> b.Config:
+        return b.Config(
+            self.kind,
+            self.restart,
+            self.gamma,
+            self.gamma2,
+            self.gamma_grad_div,
+            self.winv_mode,
+            self.mp_inv_mode,
+            int(self.aug_explicit),
+            int(self.grad_div_in_operator),
+            self.inner_prec,
+            self.device,
+            int(self.use_graphs),
+            self.exact_mass_max_its,
+            self.outer.c(),
+            self.inner.c(),
+            self.mass.c(),
+        )
+
+
+class ALContext:
+    """One solver context: matrices + hierarchy on the device, vmult-style calls."""
+
+    def __init__(self, config: ALConfig, api: b.Api | None = None):
+        if api is None:
+            from .lib import load
+
+            api = load()
+        self.api = api
+        self.config = config
+        self._h = C.c_void_p()
+        cfg = config.c()
+        st = api.create(C.byref(self._h), C.byref(cfg))
+        if st != b.OK:
+            raise FdalError(st, "fdal_create failed")
+        self._finalized = False
+        self.sizes = None
+
+    # -- lifetime ----------------------------------------------------------
+    def close(self):
+        if self._h:
+            self.api.destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st: int):
+        if st == b.OK:
+            return
+        msg = self.api.last_error(self._h)
+        msg = msg.decode() if msg else ""
+        if st in (b.ERR_INNER_NO_CONVERGENCE, b.ERR_OUTER_NO_CONVERGENCE, b.ERR_MASS_NO_CONVERGENCE):
+            raise NoConvergence(st, msg)
+        raise FdalError(st, msg)
+
+    # -- setup -------------------------------------------------------------
+    def set_csr(self, matrix_id: int, A):
+        rp, ci, v = b.csr_arrays(A)
+        self._check(
+            self.api.set_csr(
+                self._h,
+                matrix_id,
+                A.shape[0],
+                A.shape[1],
+                v.size,
+                rp.ctypes.data_as(C.POINTER(C.c_int64)),
+                ci.ctypes.data_as(C.POINTER(C.c_int32)),
+                b.dptr(v),
+            )
+        )
+
+    def set_diag(self, diag_id: int, d):
+        d = b.as_f64(d)
+        self._check(self.api.set_diag(self._h, diag_id, d.size, b.dptr(d)))
+
+    def set_amg(self, which: int, hierarchy):
+        """``hierarchy``: ``amg_setup.Hierarchy`` (levels with A, P, R, inv_diag, lambda_max)."""
+        levels = hierarchy.levels
+        for l, L in enumerate(levels[:-1]):
+            Av, ka = b.csr_view(L.A)
+            Pv, kp = b.csr_view(L.P)
+            Rv, kr = b.csr_view(L.R) if L.R is not None else (None, None)
+            idg = b.as_f64(L.inv_diag) if L.inv_diag is not None else None
+            self._check(
+                self.api.amg_set_level(
+                    self._h,
+                    which,
+                    l,
+                    C.byref(Av),
+                    C.byref(Pv),
+                    C.byref(Rv) if Rv is not None else None,
+                    b.dptr(idg) if idg is not None else None,
+                    float(L.lambda_max),
+                    int(hierarchy.cheb_degree),
+                    float(hierarchy.eig_ratio),
+                )
+            )
+        Av, ka = b.csr_view(levels[-1].A)
+        self._check(self.api.amg_set_coarse(self._h, which, len(levels) - 1, C.byref(Av)))
+
+    def finalize(self):
+        self._check(self.api.finalize(self._h))
+        sizes = (C.c_int64 * 3)()
+        nb = C.c_int()
+        self._check(self.api.block_sizes(self._h, C.byref(sizes), C.byref(nb)))
+        self.sizes = tuple(int(s) for s in sizes[: nb.value])
+        self.N = sum(self.sizes)
+        self._finalized = True
+
+    # -- vmult-style calls ----------------------------------------------------
+    def _out(self, n):
+        return np.empty(n, dtype=np.float64)
+
+    def spmv(self, matrix_id: int, x, transpose=False, n_out=None):
+        x = b.as_f64(x)
+        y = self._out(n_out)
+        self._check(self.api.spmv(self._h, matrix_id, int(transpose), b.dptr(x), b.dptr(y)))
+        return y
+
+    def apply_aug(self, x, which=b.AMG_A11):
+        x = b.as_f64(x)
+        y = self._out(x.size)
+        self._check(self.api.apply_aug(self._h, which, b.dptr(x), b.dptr(y)))
+        return y
+
+    def apply_system(self, x):
+        x = b.as_f64(x)
+        assert x.size == self.N
+        y = self._out(self.N)
+        self._check(self.api.apply_system(self._h, b.dptr(x), b.dptr(y)))
+        return y
+
+    def apply_winv(self, x):
+        x = b.as_f64(x)
+        y = self._out(x.size)
+        self._check(self.api.apply_winv(self._h, b.dptr(x), b.dptr(y)))
+        return y
+
+    def apply_mp_inv(self, x):
+        x = b.as_f64(x)
+        y = self._out(x.size)
+        its = C.c_int()
+        self._check(self.api.apply_mp_inv(self._h, b.dptr(x), b.dptr(y), C.byref(its)))
+        return y, its.value
+
+    def apply_amg(self, r, which=b.AMG_A11):
+        r = b.as_f64(r)
+        z = self._out(r.size)
+        self._check(self.api.apply_amg(self._h, which, b.dptr(r), b.dptr(z)))
+        return z
+
+    def apply_aug_inv(self, rhs, which=b.AMG_A11):
+        rhs = b.as_f64(rhs)
+        x = self._out(rhs.size)
+        its = C.c_int()
+        self._check(self.api.apply_aug_inv(self._h, which, b.dptr(rhs), b.dptr(x), C.byref(its)))
+        return x, its.value
+
+    def apply_prec(self, u):
+        u = b.as_f64(u)
+        assert u.size == self.N
+        v = self._out(self.N)
+        its = (C.c_int * 2)()
+        self._check(self.api.apply_prec(self._h, b.dptr(u), b.dptr(v), C.byref(its)))
+        return v, (its[0], its[1])
+
+    def augment_rhs(self, rhs):
+        rhs = b.as_f64(rhs).copy()
+        self._check(self.api.augment_rhs(self._h, b.dptr(rhs)))
+        return rhs
+
+    def solve(self, rhs, x0=None, raise_on_failure=True):
+        rhs = b.as_f64(rhs)
+        assert rhs.size == self.N
+        x = np.zeros(self.N) if x0 is None else b.as_f64(x0).copy()
+        info = b.SolveInfo()
+        st = self.api.solve(self._h, b.dptr(rhs), b.dptr(x), C.byref(info))
+        if st != b.OK and raise_on_failure:
+            self._check(st)
+        return x, info
+
+    # -- device-pointer variants (CUDA library only) --------------------------------
+    def solve_dev(self, d_rhs: int, d_x: int, raise_on_failure=True):
+        info = b.SolveInfo()
+        st = self.api.solve_dev(self._h, d_rhs, d_x, C.byref(info))
+        if st != b.OK and raise_on_failure:
+            self._check(st)
+        return info
+
+    def time_kernel(self, what: int, param=0, warmup=3, reps=20, flush_l2=True):
+        ms = C.c_double()
+        by = C.c_double()
+        nl = C.c_int64()
+        self._check(
+            self.api.time_kernel(
+                self._h, what, param, warmup, reps, int(flush_l2), C.byref(ms), C.byref(by), C.byref(nl)
+            )
+        )
+        return ms.value, by.value, nl.value

@@ -1,0 +1,283 @@
+/*
+ * fdal.h — C ABI of the B200-native augmented-Lagrangian (AL) solve path.
+ *
+ * This is the drop-in boundary for the ONE hot path of
+ * fdrmrc/fictitious_domain_AL_preconditioners: everything executed inside
+ *     solver_fgmres.solve(AA, x, b, P_AL)
+ * of immersed_laplace / stokes_immersed_boundary / elliptic_interface.
+ * The host application (deal.II) keeps meshing, FE assembly and the
+ * NonMatching coupling; it hands over CSR blocks, W^-1 and the AMG hierarchy
+ * through the setters below and then calls either the per-vmult entry points
+ * (parity mode, one host<->device round trip per call) or fdal_solve (the
+ * whole outer Krylov solve stays on the device).
+ *
+ * Every entry point cites the reference interface it replaces
+ * (file:line relative to the reference repository root).
+ *
+ * Conventions
+ *   - plain pointers and sizes only, no C++ / torch types; never throws.
+ *   - all functions return an int status (FDAL_OK == 0); a human readable
+ *     message for the last failure is available from fdal_last_error().
+ *   - matrices are CSR: int64 row_ptr[n_rows+1], int32 col[nnz], double
+ *     val[nnz]; entries within a row may come in any order (deal.II stores the
+ *     diagonal first, reference SURVEY A.7) — the library keeps the order it
+ *     is given, so floating-point summation order is the caller's order.
+ *   - host-pointer calls copy their arguments; the caller's arrays only need
+ *     to live for the duration of the call.
+ *   - block vectors are passed as ONE contiguous array [block0|block1|block2]
+ *     (deal.II BlockVector blocks are separate contiguous arrays; the adapter
+ *     in INTEGRATION.md copies block-wise).
+ *   - one host thread per context; a context owns its CUDA stream.
+ */
+#ifndef FDAL_H
+#define FDAL_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fdal_ctx fdal_ctx;
+
+/* ---- status codes ------------------------------------------------------ */
+enum {
+  FDAL_OK = 0,
+  FDAL_ERR_INVALID = 1,        /* bad argument / enum value                  */
+  FDAL_ERR_SHAPE = 2,          /* inconsistent matrix / vector sizes         */
+  FDAL_ERR_ALLOC = 3,          /* host or device allocation failed           */
+  FDAL_ERR_CUDA = 4,           /* CUDA runtime error                         */
+  FDAL_ERR_STATE = 5,          /* call order (e.g. solve before finalize)    */
+  FDAL_ERR_INNER_NO_CONVERGENCE = 6, /* inner CG hit max steps: deal.II would
+                                  throw SolverControl::NoConvergence
+                                  (immersed_laplace.cc:907-912)              */
+  FDAL_ERR_OUTER_NO_CONVERGENCE = 7, /* outer FGMRES/MinRes hit max steps    */
+  FDAL_ERR_MASS_NO_CONVERGENCE = 8,  /* Mp^-1 CG (stokes_immersed_boundary.cc
+                                  :934-957) hit max steps                    */
+  FDAL_ERR_NCCL = 9,
+  FDAL_ERR_UNSUPPORTED = 10
+};
+
+/* ---- which saddle-point system / preconditioner ------------------------ */
+enum {
+  /* [[Ag,Ct],[C,0]], P = BlockPreconditionerAugmentedLagrangian
+     (augmented_lagrangian_preconditioner.h:14-42, immersed_laplace.cc:891-944).
+     blocks: (n | m) */
+  FDAL_KIND_LAPLACE = 0,
+  /* [[Ag,Bt,Ct],[B,0,0],[C,0,0]], P = ...AugmentedLagrangianStokes + FGMRES
+     (augmented_lagrangian_preconditioner.h:44-79,
+      stokes_immersed_boundary.cc:1000-1074). blocks: (n_u | n_p | m) */
+  FDAL_KIND_STOKES = 1,
+  /* same system, SPD block-diagonal P + MinRes
+     (augmented_lagrangian_preconditioner.h:81-110,
+      stokes_immersed_boundary.cc:1056-1064) */
+  FDAL_KIND_STOKES_DIAG_MINRES = 2,
+  /* elliptic interface 3x3, "ideal" AL: block CG on the 2x2 augmented block
+     (augmented_lagrangian_preconditioner.h:115-164, elliptic_interface.cc:908-948).
+     blocks: (n | m2 | m), m2 == m */
+  FDAL_KIND_ELLIPTIC_IDEAL = 3,
+  /* elliptic interface 3x3, modified AL: two scalar inner solves
+     (augmented_lagrangian_preconditioner.h:168-238, elliptic_interface.cc:871-906) */
+  FDAL_KIND_ELLIPTIC_MODIFIED = 4
+};
+
+/* ---- matrices the host exports ------------------------------------------ */
+enum {
+  FDAL_MAT_A = 0,   /* (1,1) block: stiffness / velocity block (n x n)        */
+  FDAL_MAT_A2 = 1,  /* elliptic: immersed stiffness (beta2-beta1)(grad,grad)  */
+  FDAL_MAT_BT = 2,  /* Stokes: B^T (n_u x n_p) — stokes_matrix.block(0,1)     */
+  FDAL_MAT_B = 3,   /* Stokes: B (n_p x n_u)  — optional, else transposed Bt  */
+  FDAL_MAT_CT = 4,  /* coupling_matrix as the reference stores it (n x m)     */
+  FDAL_MAT_C = 5,   /* optional explicit C (m x n), else transposed Ct        */
+  FDAL_MAT_M = 6,   /* immersed mass matrix (m x m)                           */
+  FDAL_MAT_MP = 7,  /* Stokes pressure mass matrix (n_p x n_p)                */
+  FDAL_MAT_COUNT = 8
+};
+
+/* ---- W^-1 (augmented_lagrangian_preconditioner.h `invW`) --------------- */
+enum {
+  FDAL_WINV_DIAG = 0,            /* DiagonalMatrix given by fdal_set_diag     */
+  FDAL_WINV_EXACT_M = 1,         /* M^-1      (UMFPACK in the reference)      */
+  FDAL_WINV_EXACT_M_SQUARED = 2  /* M^-1 M^-1 (immersed_laplace.cc:875-876)   */
+};
+enum {
+  FDAL_MPINV_CG_LUMPED = 0, /* CG(Mp; diag(Mp*1)^-1) stokes_immersed_boundary.cc:946-957 */
+  FDAL_MPINV_EXACT = 1      /* UMFPACK in the reference (:960-962)             */
+};
+enum { FDAL_DIAG_W_INV = 0, FDAL_DIAG_MP_LUMPED_INV = 1 };
+enum { FDAL_PREC_AMG = 0, FDAL_PREC_IDENTITY = 1 };
+enum { FDAL_AMG_A11 = 0, FDAL_AMG_A22 = 1 };
+
+/* ---- deal.II SolverControl family -------------------- */
+enum {
+  FDAL_CONTROL_SOLVER = 0,    /* success: value <= tol; failure: step >= max  */
+  FDAL_CONTROL_REDUCTION = 1, /* also success: value < reduce * initial       */
+  FDAL_CONTROL_ITERATION_NUMBER = 2 /* success when step >= max               */
+};
+typedef struct fdal_control {
+  int32_t type;
+  int32_t max_steps;
+  double tol;
+  double reduce;
+} fdal_control;
+
+typedef struct fdal_config {
+  int32_t kind;        /* FDAL_KIND_*                                         */
+  int32_t restart;     /* FGMRES max_basis_size: 30 default, 50 elliptic
+                          (elliptic_interface.cc:863)                        */
+  double gamma;        /* AL gamma (gamma_1); any 1/h, 1/h^2 scaling already
+                          applied by the caller (immersed_laplace.cc:655-657,
+                          elliptic_interface.cc:743-753)                     */
+  double gamma2;       /* elliptic gamma_2                                    */
+  double gamma_grad_div; /* Stokes gamma_grad_div                             */
+  int32_t winv_mode;   /* FDAL_WINV_*                                         */
+  int32_t mp_inv_mode; /* FDAL_MPINV_*                                        */
+  int32_t aug_explicit; /* 1: operator form, A already contains the AL term
+                           (immersed_laplace.cc:882)                         */
+  int32_t grad_div_in_operator; /* 1: Aug += gamma_gd Bt Mp^-1 B
+                           (stokes_immersed_boundary.cc:995)                 */
+  int32_t inner_prec;  /* FDAL_PREC_AMG | FDAL_PREC_IDENTITY                  */
+  int32_t device;      /* CUDA device ordinal                                 */
+  int32_t use_graphs;  /* replay the V-cycle / CG iteration as CUDA graphs    */
+  int32_t exact_mass_max_its; /* cap for the device mass solve (0 = default)  */
+  fdal_control outer;  /* outer FGMRES / MinRes control                       */
+  fdal_control inner;  /* inner CG on A_gamma (and on A22_gamma)              */
+  fdal_control mass;   /* Mp^-1 CG control: (100, 1e-6)                       */
+} fdal_config;
+
+#define FDAL_MAX_HISTORY 1024
+typedef struct fdal_solve_info {
+  int32_t status;            /* FDAL_OK or the failure code                   */
+  int32_t outer_iterations;  /* SolverControl::last_step()                    */
+  int32_t inner_iterations;  /* sum over all inner A_gamma (A11) CG solves    */
+  int32_t inner_iterations_a22; /* sum over A22_gamma solves (elliptic)       */
+  int32_t inner_solves;      /* number of Aug_inv applications                */
+  int32_t mass_iterations;   /* sum over Mp^-1 CG solves                      */
+  int32_t n_history;         /* valid entries of residual_history             */
+  int32_t reserved;
+  double initial_residual;
+  double final_residual;
+  double solve_ms;           /* device time of the solve (CUDA events)        */
+  int64_t kernel_launches;   /* kernels of this library launched in the solve */
+  double residual_history[FDAL_MAX_HISTORY];
+} fdal_solve_info;
+
+/* ---- lifetime ------------------------------------------------------------ */
+int fdal_create(fdal_ctx **out, const fdal_config *cfg);
+void fdal_destroy(fdal_ctx *ctx);
+const char *fdal_last_error(const fdal_ctx *ctx);
+const char *fdal_version(void);
+
+/* ---- setup: replaces the linear_operator(...) wrappers ------------------- *
+ * immersed_laplace.cc:638-643, stokes_immersed_boundary.cc:923-929,
+ * elliptic_interface.cc:680-687 */
+int fdal_set_csr(fdal_ctx *ctx, int matrix_id, int64_t n_rows, int64_t n_cols,
+                 int64_t nnz, const int64_t *row_ptr, const int32_t *col,
+                 const double *val);
+/* DiagonalMatrix payloads: inverse_squares / inv_diagonal
+ * (immersed_laplace.cc:853-873, stokes_immersed_boundary.cc:946-983,
+ *  elliptic_interface.cc:705-728, utilities.h:348-374) */
+int fdal_set_diag(fdal_ctx *ctx, int diag_id, int64_t n, const double *d);
+
+/* AMG hierarchy built by TrilinosWrappers::PreconditionAMG::initialize
+ * (immersed_laplace.cc:704,833; utilities.h:308-317,729-733;
+ *  elliptic_interface.cc:824-850).  Level 0 = finest.  `P` maps level+1 ->
+ * level (n_l x n_{l+1}); `R` may be NULL (then R = P^T).  inv_diag may be NULL
+ * (then 1/diag(A)).  Chebyshev: degree sweeps, eigenvalue interval
+ * [lambda_max/eig_ratio, 1.1*lambda_max].
+ * The last level set is the coarsest: it only needs A (direct solve). */
+typedef struct fdal_csr_view {
+  int64_t n_rows, n_cols, nnz;
+  const int64_t *row_ptr;
+  const int32_t *col;
+  const double *val;
+} fdal_csr_view;
+int fdal_amg_set_level(fdal_ctx *ctx, int which, int level,
+                       const fdal_csr_view *A, const fdal_csr_view *P,
+                       const fdal_csr_view *R, const double *inv_diag,
+                       double lambda_max, int cheb_degree, double eig_ratio);
+int fdal_amg_set_coarse(fdal_ctx *ctx, int which, int level,
+                        const fdal_csr_view *A);
+
+/* upload, build transposes / kernel schedules, allocate the Krylov workspace */
+int fdal_finalize(fdal_ctx *ctx);
+
+/* sizes of the blocks of the system vector, n_blocks in {2,3} */
+int fdal_block_sizes(const fdal_ctx *ctx, int64_t sizes[3], int *n_blocks);
+
+/* ---- per-vmult entry points (host pointers) ------------------------------ */
+/* SparseMatrix::vmult / Tvmult on an exported block (K1/K2/K6/K7) */
+int fdal_spmv(fdal_ctx *ctx, int matrix_id, int transpose, const double *x,
+              double *y);
+/* Aug.vmult: y = A x + gamma Ct W^-1 C x  (immersed_laplace.cc:880-884,
+ * stokes_immersed_boundary.cc:991-995, elliptic_interface.cc:807); which =
+ * FDAL_AMG_A11 for A_gamma / A11_gamma, FDAL_AMG_A22 for A22_gamma (:810) */
+int fdal_apply_aug(fdal_ctx *ctx, int which, const double *x, double *y);
+/* AA.vmult / system_operator.vmult (immersed_laplace.cc:891-892,
+ * stokes_immersed_boundary.cc:1000-1003, elliptic_interface.cc:816-819) */
+int fdal_apply_system(fdal_ctx *ctx, const double *x, double *y);
+/* invW.vmult */
+int fdal_apply_winv(fdal_ctx *ctx, const double *x, double *y);
+/* Mp_inv.vmult (stokes_immersed_boundary.cc:931-963) */
+int fdal_apply_mp_inv(fdal_ctx *ctx, const double *x, double *y, int *its);
+/* TrilinosWrappers::PreconditionAMG::vmult — one V-cycle */
+int fdal_apply_amg(fdal_ctx *ctx, int which, const double *r, double *z);
+/* Aug_inv.vmult = inverse_operator(Aug, SolverCG, AMG) from a zero guess
+ * (immersed_laplace.cc:911-912, stokes_immersed_boundary.cc:1045,
+ *  elliptic_interface.cc:895-898) */
+int fdal_apply_aug_inv(fdal_ctx *ctx, int which, const double *b, double *x,
+                       int *its);
+/* P.vmult of the configured AL preconditioner
+ * (augmented_lagrangian_preconditioner.h:28-34, 62-70, 95-103, 130-156, 186-229).
+ * inner_its[0] = A11 CG iterations, inner_its[1] = A22 CG iterations. */
+int fdal_apply_prec(fdal_ctx *ctx, const double *u, double *v, int inner_its[2]);
+/* rhs0 = f + gamma Ct W^-1 g (immersed_laplace.cc:899-905,
+ * stokes_immersed_boundary.cc:1011-1018): in-place on the block rhs */
+int fdal_augment_rhs(fdal_ctx *ctx, double *rhs_inout);
+
+/* ---- the solve: replaces solver_fgmres.solve(AA, x, b, P) ----------------
+ * immersed_laplace.cc:943-944, stokes_immersed_boundary.cc:1063-1074,
+ * elliptic_interface.cc:905,947.  x_inout holds the initial guess. */
+int fdal_solve(fdal_ctx *ctx, const double *rhs, double *x_inout,
+               fdal_solve_info *info);
+
+/* ---- device-pointer variants (inputs already resident in HBM) ------------ */
+int fdal_solve_dev(fdal_ctx *ctx, const double *d_rhs, double *d_x_inout,
+                   fdal_solve_info *info);
+int fdal_apply_aug_dev(fdal_ctx *ctx, int which, const double *d_x, double *d_y);
+int fdal_apply_amg_dev(fdal_ctx *ctx, int which, const double *d_r, double *d_z);
+int fdal_spmv_dev(fdal_ctx *ctx, int matrix_id, int transpose, const double *d_x,
+                  double *d_y);
+
+/* ---- measurement: CUDA-event timing of one kernel family on the ctx stream */
+enum {
+  FDAL_TIME_SPMV_A = 0,     /* y = A x                                        */
+  FDAL_TIME_AUG = 1,        /* y = A x + gamma Ct W^-1 C x (diag W^-1)        */
+  FDAL_TIME_VCYCLE = 2,     /* one AMG V-cycle (which = A11)                  */
+  FDAL_TIME_CHEB_FINE = 3,  /* one fused Chebyshev step on the finest level   */
+  FDAL_TIME_DOT = 4,        /* fused dot on an N-vector                       */
+  FDAL_TIME_MULTIDOT = 5,   /* V^T w with `param` basis vectors               */
+  FDAL_TIME_AXPY = 6
+};
+/* runs `reps` launches after `warmup`, optionally flushing L2 between them;
+ * returns average ms and the algorithmic bytes of one launch */
+int fdal_time_kernel(fdal_ctx *ctx, int what, int param, int warmup, int reps,
+                     int flush_l2, double *avg_ms, double *algorithmic_bytes,
+                     int64_t *launches_per_rep);
+
+/* ---- multi-GPU (one process per GPU) -------------------------------------
+ * No reference counterpart (the reference is serial).  Rows of the
+ * background unknowns are partitioned; the multiplier block is replicated. */
+int fdal_nccl_unique_id(char id_out[128]);
+int fdal_comm_init(fdal_ctx *ctx, const char id[128], int rank, int n_ranks);
+/* halo plan of a row-partitioned matrix whose columns are numbered
+ * [owned | halo]: for each peer the owned entries to send and the number of
+ * halo entries received (halo entries are ordered by peer rank). */
+int fdal_set_halo(fdal_ctx *ctx, int matrix_id, int level, int which,
+                  int64_t n_owned_cols, int64_t n_halo, const int32_t *send_counts,
+                  const int32_t *send_idx, const int32_t *recv_counts);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FDAL_H */
