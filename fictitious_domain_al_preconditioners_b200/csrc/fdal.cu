@@ -1,0 +1,1626 @@
+// fdal.cu — context, device-resident solve drivers and the C ABI (include/fdal.h).
+//
+// Layout in HBM: every matrix is CSR with int32 row_ptr/col and FP64 values in
+// three plain arrays (entries kept in the caller's order); the block system vector
+// is ONE contiguous array [block0|block1|block2]; the FGMRES bases V (restart+1)
+// and Z (restart) are column-major N x k slabs; AMG levels own x/b/r/d scratch.
+// All per-iteration work is enqueued on the context's stream; the host only reads
+// back one scalar per inner CG iteration (the residual norm deal.II's SolverControl
+// tests) and the Hessenberg column per outer iteration.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/fdal.h"
+#include "kernels.cuh"
+
+namespace fdal {
+
+// ------------------------------------------------------------------ host CSR
+struct HostCsr {
+  int64_t nr = 0, nc = 0, nnz = 0;
+  std::vector<int> rp, ci;
+  std::vector<double> v;
+  bool set = false;
+};
+static void host_transpose(const HostCsr &A, HostCsr &T) {
+  // stable counting sort: within a row of T columns ascend, i.e. the same
+  // accumulation order as SparseMatrix::Tvmult's row scatter
+  T.nr = A.nc;
+  T.nc = A.nr;
+  T.nnz = A.nnz;
+  T.rp.assign(T.nr + 1, 0);
+  T.ci.resize(A.nnz);
+  T.v.resize(A.nnz);
+  for (int64_t k = 0; k < A.nnz; ++k) T.rp[A.ci[k] + 1]++;
+  for (int64_t i = 0; i < T.nr; ++i) T.rp[i + 1] += T.rp[i];
+  std::vector<int> pos(T.rp.begin(), T.rp.end() - 1);
+  for (int64_t i = 0; i < A.nr; ++i)
+    for (int k = A.rp[i]; k < A.rp[i + 1]; ++k) {
+      const int q = pos[A.ci[k]]++;
+      T.ci[q] = (int)i;
+      T.v[q] = A.v[k];
+    }
+  T.set = true;
+}
+
+struct DevCsr {
+  CsrDev d;
+  int *rp = nullptr, *ci = nullptr;
+  double *v = nullptr;
+  bool set = false;
+};
+
+struct AmgLevel {
+  HostCsr hA, hP, hR;
+  std::vector<double> h_invd;
+  DevCsr A, P, R;
+  double *invd = nullptr;
+  double lmax = 1.0, ratio = 10.0;
+  int degree = 2;
+  int n = 0;
+  double *xa = nullptr, *xb = nullptr, *b = nullptr, *r = nullptr, *d = nullptr;
+};
+struct Amg {
+  std::vector<AmgLevel> lev;
+  double *cinv = nullptr;
+  bool ready = false;
+};
+
+struct ControlState {
+  fdal_control c;
+  double initial = 0, reduced_tol = 0;
+  int last_step = 0;
+  double last_value = 0;
+};
+enum { ST_ITERATE = 0, ST_SUCCESS = 1, ST_FAILURE = 2 };
+static int control_check(ControlState &s, int step, double val) {
+  s.last_step = step;
+  s.last_value = val;
+  if (s.c.type == FDAL_CONTROL_REDUCTION) {
+    if (step == 0) {
+      s.initial = val;
+      s.reduced_tol = val * s.c.reduce;
+    }
+    if (val < s.reduced_tol) return ST_SUCCESS;
+  } else if (s.c.type == FDAL_CONTROL_ITERATION_NUMBER) {
+    if (step >= s.c.max_steps) return ST_SUCCESS;
+  }
+  if (val <= s.c.tol) return ST_SUCCESS;
+  if (step >= s.c.max_steps || std::isnan(val)) return ST_FAILURE;
+  return ST_ITERATE;
+}
+
+struct CgWs {
+  int64_t n = 0;
+  double *r = nullptr, *z = nullptr, *p = nullptr, *v = nullptr;
+  double *scal = nullptr;  // S_COUNT device scalars
+};
+
+}  // namespace fdal
+
+using namespace fdal;
+
+struct fdal_ctx {
+  fdal_config cfg;
+  int sms = 148;
+  cudaStream_t stream = nullptr;
+  HostCsr hmat[FDAL_MAT_COUNT];
+  DevCsr dmat[FDAL_MAT_COUNT];
+  std::vector<double> h_winv, h_mp_lumped;
+  double *d_winv = nullptr, *d_mp_lumped = nullptr, *d_m_invdiag = nullptr, *d_mp_invdiag = nullptr;
+  Amg amg[2];
+  bool finalized = false;
+  int64_t n0 = 0, n1 = 0, n2 = 0, N = 0, m = 0;
+  int nblocks = 0;
+  // reductions
+  double *d_partials = nullptr;
+  unsigned int *d_counter = nullptr;
+  double *d_scal = nullptr;   // general scratch scalars (128)
+  double *h_scal = nullptr;   // pinned mirror (128)
+  // workspaces
+  CgWs cg11, cg22, cgblk, cgmass_m, cgmass_p;
+  double *t_m0 = nullptr, *t_m1 = nullptr, *t_m2 = nullptr, *t_mw = nullptr;  // m-vectors
+  double *t_n0 = nullptr;                                     // n0-vector
+  double *t_p0 = nullptr, *t_p1 = nullptr;                    // n1-vectors
+  double *t_N0 = nullptr, *t_N1 = nullptr;                    // N-vectors (API staging)
+  double *V = nullptr, *Z = nullptr, *d_h = nullptr, *d_y = nullptr;
+  double *mr_u[3] = {nullptr, nullptr, nullptr}, *mr_m[3] = {nullptr, nullptr, nullptr}, *mr_v = nullptr;
+  char *flush_buf = nullptr;
+  size_t flush_bytes = 0;
+  int mass_its_m = 0, mass_its_p = 0;  // calibrated fixed iteration counts (exact mass solves)
+  // counters
+  int its_a11 = 0, its_a22 = 0, its_mass = 0, n_inner_solves = 0;
+  int64_t launches = 0;
+  int fail = 0;
+  std::vector<void *> allocs;
+  std::string err;
+};
+
+namespace fdal {
+
+static void set_err(fdal_ctx *c, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  c->err = buf;
+}
+#define CU(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess) {                                                              \
+      set_err(c, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(e_), __FILE__, __LINE__, #call); \
+      return FDAL_ERR_CUDA;                                                               \
+    }                                                                                     \
+  } while (0)
+
+template <class T>
+static int dmalloc(fdal_ctx *c, T **p, size_t count) {
+  void *q = nullptr;
+  cudaError_t e = cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T));
+  if (e != cudaSuccess) {
+    set_err(c, "cudaMalloc of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
+    return FDAL_ERR_ALLOC;
+  }
+  c->allocs.push_back(q);
+  *p = (T *)q;
+  return FDAL_OK;
+}
+static int dvec(fdal_ctx *c, double **p, int64_t n) {
+  int st = dmalloc(c, p, (size_t)std::max<int64_t>(n, 1));
+  if (st) return st;
+  CU(cudaMemsetAsync(*p, 0, (size_t)std::max<int64_t>(n, 1) * sizeof(double), c->stream));
+  return FDAL_OK;
+}
+
+static int choose_tpr(double avg) {
+  static const char *env = getenv("FDAL_TPR");
+  if (env) {
+    int t = atoi(env);
+    if (t == 2 || t == 4 || t == 8 || t == 16 || t == 32) return t;
+  }
+  if (avg <= 2.5) return 2;
+  if (avg <= 6.0) return 4;
+  if (avg <= 14.0) return 8;
+  if (avg <= 40.0) return 16;
+  return 32;
+}
+
+static int upload_csr(fdal_ctx *c, const HostCsr &h, DevCsr &d) {
+  if (h.nnz >= (int64_t)std::numeric_limits<int>::max() || h.nr >= (int64_t)std::numeric_limits<int>::max()) {
+    set_err(c, "matrix with %lld nnz exceeds the 32-bit row_ptr of this build", (long long)h.nnz);
+    return FDAL_ERR_UNSUPPORTED;
+  }
+  int st;
+  if ((st = dmalloc(c, &d.rp, (size_t)h.nr + 1))) return st;
+  if ((st = dmalloc(c, &d.ci, (size_t)h.nnz))) return st;
+  if ((st = dmalloc(c, &d.v, (size_t)h.nnz))) return st;
+  CU(cudaMemcpyAsync(d.rp, h.rp.data(), ((size_t)h.nr + 1) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  if (h.nnz) {
+    CU(cudaMemcpyAsync(d.ci, h.ci.data(), (size_t)h.nnz * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d.v, h.v.data(), (size_t)h.nnz * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  d.d.nrows = (int)h.nr;
+  d.d.ncols = (int)h.nc;
+  d.d.nnz = h.nnz;
+  d.d.rp = d.rp;
+  d.d.ci = d.ci;
+  d.d.v = d.v;
+  d.d.tpr = choose_tpr(h.nr ? (double)h.nnz / (double)h.nr : 1.0);
+  d.set = true;
+  return FDAL_OK;
+}
+
+// ------------------------------------------------------------------ launch helpers
+static inline int grid_rows(const fdal_ctx *c, long long nrows, int tpr) {
+  const long long rpb = kBlock / tpr;
+  long long g = (nrows + rpb - 1) / rpb;
+  return (int)std::max<long long>(1, std::min<long long>(g, (long long)c->sms * kMaxGridPerSM));
+}
+static inline int grid_elems(const fdal_ctx *c, long long n) {
+  long long g = (n + kBlock - 1) / kBlock;
+  return (int)std::max<long long>(1, std::min<long long>(g, (long long)c->sms * kMaxGridPerSM));
+}
+static inline Reducer reducer(fdal_ctx *c, double *out) { return Reducer{c->d_partials, c->d_counter, out}; }
+static inline XVec xv(const double *x) { return XVec{x, nullptr, std::numeric_limits<int>::max()}; }
+
+template <class Epi>
+static void spmv(fdal_ctx *c, const DevCsr &A, const double *x, Epi epi, double *red_out = nullptr) {
+  if (A.d.nrows == 0) return;
+  const int g = grid_rows(c, A.d.nrows, A.d.tpr);
+  Reducer R = reducer(c, red_out);
+  XVec X = xv(x);
+  switch (A.d.tpr) {
+    case 2: k_spmv<2, Epi><<<g, kBlock, 0, c->stream>>>(A.d, X, epi, R); break;
+    case 4: k_spmv<4, Epi><<<g, kBlock, 0, c->stream>>>(A.d, X, epi, R); break;
+    case 8: k_spmv<8, Epi><<<g, kBlock, 0, c->stream>>>(A.d, X, epi, R); break;
+    case 16: k_spmv<16, Epi><<<g, kBlock, 0, c->stream>>>(A.d, X, epi, R); break;
+    default: k_spmv<32, Epi><<<g, kBlock, 0, c->stream>>>(A.d, X, epi, R); break;
+  }
+  c->launches++;
+}
+template <class Epi>
+static void spmv2(fdal_ctx *c, const DevCsr &A, const double *x, const DevCsr &Ct, const double *t, Epi epi,
+                  double *red_out = nullptr) {
+  if (A.d.nrows == 0) return;
+  const int g = grid_rows(c, A.d.nrows, A.d.tpr);
+  Reducer R = reducer(c, red_out);
+  XVec X = xv(x);
+  switch (A.d.tpr) {
+    case 2: k_spmv2<2, Epi><<<g, kBlock, 0, c->stream>>>(A.d, X, Ct.d, t, epi, R); break;
+    case 4: k_spmv2<4, Epi><<<g, kBlock, 0, c->stream>>>(A.d, X, Ct.d, t, epi, R); break;
+    case 8: k_spmv2<8, Epi><<<g, kBlock, 0, c->stream>>>(A.d, X, Ct.d, t, epi, R); break;
+    case 16: k_spmv2<16, Epi><<<g, kBlock, 0, c->stream>>>(A.d, X, Ct.d, t, epi, R); break;
+    default: k_spmv2<32, Epi><<<g, kBlock, 0, c->stream>>>(A.d, X, Ct.d, t, epi, R); break;
+  }
+  c->launches++;
+}
+static void dot(fdal_ctx *c, int64_t n, const double *a, const double *b, double *out) {
+  k_dot<<<grid_elems(c, n), kBlock, 0, c->stream>>>(n, a, b, reducer(c, out));
+  c->launches++;
+}
+static void axpby(fdal_ctx *c, int64_t n, double a, const double *x, double b, double *y) {
+  if (n == 0) return;
+  k_axpby<<<grid_elems(c, n), kBlock, 0, c->stream>>>(n, a, x, b, y);
+  c->launches++;
+}
+static void dscale(fdal_ctx *c, int64_t n, double a, double *y) {  // y *= a
+  if (n == 0 || a == 1.0) return;
+  k_axpby<<<grid_elems(c, n), kBlock, 0, c->stream>>>(n, a, y, 0.0, y);
+  c->launches++;
+}
+static void diag_scale(fdal_ctx *c, int64_t n, double a, const double *d, const double *x, double *y) {
+  if (n == 0) return;
+  k_diag_scale<<<grid_elems(c, n), kBlock, 0, c->stream>>>(n, a, d, x, y);
+  c->launches++;
+}
+static void dcopy(fdal_ctx *c, int64_t n, const double *x, double *y) {
+  if (n && x != y) cudaMemcpyAsync(y, x, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream);
+}
+static void dzero(fdal_ctx *c, int64_t n, double *y) {
+  if (n) cudaMemsetAsync(y, 0, (size_t)n * sizeof(double), c->stream);
+}
+// read device scalars to the host (one sync)
+static int read_scalars(fdal_ctx *c, const double *d, int count, double *out) {
+  CU(cudaMemcpyAsync(c->h_scal, d, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  memcpy(out, c->h_scal, (size_t)count * sizeof(double));
+  return FDAL_OK;
+}
+
+// ------------------------------------------------------------------ AMG V-cycle (K8)
+static void cheb_coeffs(const AmgLevel &L, double &theta, double &delta, double &s1) {
+  const double beta = 1.1 * L.lmax, alpha = L.lmax / L.ratio;
+  delta = 0.5 * (beta - alpha);
+  theta = 0.5 * (beta + alpha);
+  s1 = theta / delta;
+}
+// Chebyshev(degree) on level L: zero_guess -> result in *xcur; returns the buffer
+// holding the result.  final_out (optional): the last step writes there (and fuses
+// dot(b, x) into red_out when given).
+static double *cheb(fdal_ctx *c, AmgLevel &L, const double *b, double *xcur, bool zero_guess, double *final_out,
+                    double *red_out) {
+  double theta, delta, s1;
+  cheb_coeffs(L, theta, delta, s1);
+  double rho = 1.0 / s1;
+  const int n = L.n;
+  int k = 0;
+  double *cur = xcur;
+  auto other = [&](double *p) { return p == L.xa ? L.xb : L.xa; };
+  if (zero_guess) {
+    double *dst = (L.degree == 1 && final_out) ? final_out : cur;
+    k_cheb_zero<<<grid_elems(c, n), kBlock, 0, c->stream>>>(n, b, L.invd, 1.0 / theta, L.d, dst);
+    c->launches++;
+    cur = dst;
+    k = 1;
+  }
+  for (; k < L.degree; ++k) {
+    const bool first = (k == 0);
+    double c1 = 0.0, c2 = 1.0 / theta;
+    if (!first) {
+      const double rho1 = 1.0 / (2.0 * s1 - rho);
+      c1 = rho1 * rho;
+      c2 = 2.0 * rho1 / delta;
+      rho = rho1;
+    }
+    const bool last = (k == L.degree - 1);
+    double *dst = (last && final_out) ? final_out : other(cur);
+    if (last && red_out) {
+      EpiCheb<true> e{b, L.invd, cur, L.d, dst, c1, c2, first ? 1 : 0};
+      spmv(c, L.A, cur, e, red_out);
+    } else {
+      EpiCheb<false> e{b, L.invd, cur, L.d, dst, c1, c2, first ? 1 : 0};
+      spmv(c, L.A, cur, e);
+    }
+    cur = dst;
+  }
+  return cur;
+}
+// z = AMG(b); optionally *red_out = b.z
+static void vcycle(fdal_ctx *c, Amg &g, const double *b0, double *z, double *red_out) {
+  const int nl = (int)g.lev.size();
+  if (nl == 1) {
+    const int n = g.lev[0].n;
+    k_gemv<<<(n * 32 + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(n, g.cinv, b0, z);
+    c->launches++;
+    if (red_out) dot(c, n, b0, z, red_out);
+    return;
+  }
+  std::vector<double *> xres(nl, nullptr);
+  for (int l = 0; l < nl - 1; ++l) {
+    AmgLevel &L = g.lev[l];
+    const double *bl = l == 0 ? b0 : L.b;
+    double *x = cheb(c, L, bl, L.xa, true, nullptr, nullptr);
+    spmv(c, L.A, x, EpiResid{L.r, bl});
+    spmv(c, L.R, L.r, EpiAssign{g.lev[l + 1].b, 1.0});
+    xres[l] = x;
+  }
+  {
+    AmgLevel &C = g.lev[nl - 1];
+    k_gemv<<<(C.n * 32 + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(C.n, g.cinv, C.b, C.xa);
+    c->launches++;
+    xres[nl - 1] = C.xa;
+  }
+  for (int l = nl - 2; l >= 0; --l) {
+    AmgLevel &L = g.lev[l];
+    const double *bl = l == 0 ? b0 : L.b;
+    spmv(c, L.P, xres[l + 1], EpiAdd{xres[l], 1.0});
+    xres[l] = cheb(c, L, bl, xres[l], false, l == 0 ? z : nullptr, l == 0 ? red_out : nullptr);
+  }
+}
+
+// ------------------------------------------------------------------ device CG (K9)
+using OpFn = std::function<void(const double *in, double *out, double *dot_out)>;
+
+static void cg_start(fdal_ctx *c, CgWs &w, const double *b, double *x) {
+  dzero(c, w.n, x);
+  dcopy(c, w.n, b, w.r);
+  dzero(c, w.n, w.p);
+  k_set_scalar<<<1, 1, 0, c->stream>>>(w.scal + S_RHO_OLD, std::numeric_limits<double>::infinity());
+  c->launches++;
+}
+// one iteration body, no host interaction (capturable)
+static void cg_body(fdal_ctx *c, CgWs &w, const OpFn &op, const OpFn &prec, double *x) {
+  const int64_t n = w.n;
+  prec(w.r, w.z, w.scal + S_RHO);
+  k_cg_update_p<<<grid_elems(c, n), kBlock, 0, c->stream>>>(n, w.z, w.p, w.scal);
+  c->launches++;
+  op(w.p, w.v, w.scal + S_PV);
+  k_cg_update_xr<<<grid_elems(c, n), kBlock, 0, c->stream>>>(n, n, w.p, w.v, x, w.r, w.scal,
+                                                               reducer(c, w.scal + S_RR));
+  c->launches++;
+}
+// deal.II SolverCG from a zero initial guess (inverse_operator), host-checked control
+static int cg_solve(fdal_ctx *c, CgWs &w, const OpFn &op, const OpFn &prec, const fdal_control &ctl, const double *b,
+                    double *x, int *its_out, int fail_code) {
+  ControlState cs;
+  cs.c = ctl;
+  cg_start(c, w, b, x);
+  dot(c, w.n, w.r, w.r, w.scal + S_RR);
+  double rr;
+  int st = read_scalars(c, w.scal + S_RR, 1, &rr);
+  if (st) return st;
+  int state = control_check(cs, 0, std::sqrt(std::fabs(rr)));
+  int it = 0;
+  while (state == ST_ITERATE) {
+    ++it;
+    cg_body(c, w, op, prec, x);
+    st = read_scalars(c, w.scal + S_RR, 1, &rr);
+    if (st) return st;
+    state = control_check(cs, it, std::sqrt(std::fabs(rr)));
+  }
+  *its_out = it;
+  return state == ST_SUCCESS ? FDAL_OK : fail_code;
+}
+// fixed-count Jacobi-PCG on a mass matrix: the device replacement of
+// SparseDirectUMFPACK::vmult (K5); no host interaction
+static void mass_prec(fdal_ctx *c, const double *invdiag, int64_t n, const double *r, double *z, double *dot_out) {
+  k_diag_prec_dot<<<grid_elems(c, n), kBlock, 0, c->stream>>>(n, invdiag, r, z, reducer(c, dot_out));
+  c->launches++;
+}
+static void mass_solve_fixed(fdal_ctx *c, CgWs &w, const DevCsr &M, const double *invdiag, int its, const double *b,
+                             double *x) {
+  cg_start(c, w, b, x);
+  OpFn op = [&](const double *in, double *out, double *d) { spmv(c, M, in, EpiDotX{out, in}, d); };
+  OpFn pr = [&](const double *r, double *z, double *d) { mass_prec(c, invdiag, w.n, r, z, d); };
+  for (int i = 0; i < its; ++i) cg_body(c, w, op, pr, x);
+}
+static int mass_calibrate(fdal_ctx *c, CgWs &w, const DevCsr &M, const double *invdiag, int *its_out) {
+  // count the iterations Jacobi-PCG needs to push the recursive residual below
+  // 1e-17 |b| on a rough right-hand side; the solve then always runs that many + 3
+  const int64_t n = w.n;
+  std::vector<double> hb((size_t)n);
+  unsigned long long s = 0x9E3779B97F4A7C15ull;
+  for (int64_t i = 0; i < n; ++i) {
+    s = s * 6364136223846793005ull + 1442695040888963407ull;
+    hb[(size_t)i] = ((double)(s >> 11) / 9007199254740992.0) * 2.0 - 1.0;
+  }
+  double *b = nullptr;
+  int st = dvec(c, &b, n);
+  if (st) return st;
+  double *x = nullptr;
+  if ((st = dvec(c, &x, n))) return st;
+  CU(cudaMemcpyAsync(b, hb.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  cg_start(c, w, b, x);
+  dot(c, n, w.r, w.r, w.scal + S_RR);
+  double rr0;
+  if ((st = read_scalars(c, w.scal + S_RR, 1, &rr0))) return st;
+  OpFn op = [&](const double *in, double *out, double *d) { spmv(c, M, in, EpiDotX{out, in}, d); };
+  OpFn pr = [&](const double *r, double *z, double *d) { mass_prec(c, invdiag, n, r, z, d); };
+  const int cap = c->cfg.exact_mass_max_its > 0 ? c->cfg.exact_mass_max_its : 300;
+  int it = 0;
+  double rr = rr0;
+  while (it < cap && std::sqrt(std::fabs(rr)) > 1e-17 * std::sqrt(rr0)) {
+    cg_body(c, w, op, pr, x);
+    ++it;
+    if ((st = read_scalars(c, w.scal + S_RR, 1, &rr))) return st;
+  }
+  *its_out = std::min(cap, it + 3);
+  return FDAL_OK;
+}
+
+// ------------------------------------------------------------------ operators of the path
+static bool is_stokes(const fdal_ctx *c) {
+  return c->cfg.kind == FDAL_KIND_STOKES || c->cfg.kind == FDAL_KIND_STOKES_DIAG_MINRES;
+}
+static bool is_elliptic(const fdal_ctx *c) {
+  return c->cfg.kind == FDAL_KIND_ELLIPTIC_IDEAL || c->cfg.kind == FDAL_KIND_ELLIPTIC_MODIFIED;
+}
+
+// y = a * invW x   (K4 / K5).  x and y must be distinct buffers (and not t_mw).
+static void apply_winv_scaled(fdal_ctx *c, double a, const double *x, double *y) {
+  const int64_t m = c->m;
+  if (c->cfg.winv_mode == FDAL_WINV_DIAG) {
+    diag_scale(c, m, a, c->d_winv, x, y);
+  } else if (c->cfg.winv_mode == FDAL_WINV_EXACT_M) {
+    mass_solve_fixed(c, c->cgmass_m, c->dmat[FDAL_MAT_M], c->d_m_invdiag, c->mass_its_m, x, y);
+    dscale(c, m, a, y);
+  } else {
+    mass_solve_fixed(c, c->cgmass_m, c->dmat[FDAL_MAT_M], c->d_m_invdiag, c->mass_its_m, x, c->t_mw);
+    mass_solve_fixed(c, c->cgmass_m, c->dmat[FDAL_MAT_M], c->d_m_invdiag, c->mass_its_m, c->t_mw, y);
+    dscale(c, m, a, y);
+  }
+}
+// Mp_inv (stokes_immersed_boundary.cc:931-963)
+static int apply_mp_inv(fdal_ctx *c, const double *x, double *y) {
+  if (c->cfg.mp_inv_mode == FDAL_MPINV_EXACT) {
+    mass_solve_fixed(c, c->cgmass_p, c->dmat[FDAL_MAT_MP], c->d_mp_invdiag, c->mass_its_p, x, y);
+    return FDAL_OK;
+  }
+  OpFn op = [&](const double *in, double *out, double *d) { spmv(c, c->dmat[FDAL_MAT_MP], in, EpiDotX{out, in}, d); };
+  OpFn pr = [&](const double *r, double *z, double *d) { mass_prec(c, c->d_mp_lumped, c->n1, r, z, d); };
+  int its = 0;
+  int st = cg_solve(c, c->cgmass_p, op, pr, c->cfg.mass, x, y, &its, FDAL_ERR_MASS_NO_CONVERGENCE);
+  c->its_mass += its;
+  if (st && !c->fail) c->fail = st;
+  return st;
+}
+
+// phase 1 of the fused augmented apply: t = a * invW (C x [- M x1m]) + add ; y1 = C x
+static void couple_phase1(fdal_ctx *c, const double *x, double a, const double *add, double *y1, double *t) {
+  const DevCsr &C = c->dmat[FDAL_MAT_C];
+  if (c->cfg.winv_mode == FDAL_WINV_DIAG) {
+    spmv(c, C, x, EpiCouple{t, c->d_winv, a, add, y1});
+  } else {
+    spmv(c, C, x, EpiCouple{c->t_m1, nullptr, 1.0, nullptr, y1});
+    apply_winv_scaled(c, a, c->t_m1, t);
+    if (add) axpby(c, c->m, 1.0, add, 1.0, t);
+  }
+}
+
+// Aug.vmult (K3): y = A x + gamma Ct invW C x  [+ gamma_gd Bt Mp^-1 B x]; optional dot x.y
+static void apply_aug11(fdal_ctx *c, const double *x, double *y, double *dot_out) {
+  const DevCsr &A = c->dmat[FDAL_MAT_A];
+  const bool gd = is_stokes(c) && c->cfg.grad_div_in_operator;
+  if (c->cfg.aug_explicit) {
+    if (dot_out && !gd)
+      spmv(c, A, x, EpiDotX{y, x}, dot_out);
+    else
+      spmv(c, A, x, EpiAssign{y, 1.0});
+  } else {
+    couple_phase1(c, x, c->cfg.gamma, nullptr, nullptr, c->t_m0);
+    if (dot_out && !gd)
+      spmv2(c, A, x, c->dmat[FDAL_MAT_CT], c->t_m0, EpiDotX{y, x}, dot_out);
+    else
+      spmv2(c, A, x, c->dmat[FDAL_MAT_CT], c->t_m0, EpiAssign{y, 1.0});
+  }
+  if (gd) {
+    spmv(c, c->dmat[FDAL_MAT_B], x, EpiAssign{c->t_p0, 1.0});
+    apply_mp_inv(c, c->t_p0, c->t_p1);
+    spmv(c, c->dmat[FDAL_MAT_BT], c->t_p1, EpiAdd{y, c->cfg.gamma_grad_div});
+    if (dot_out) dot(c, c->n0, x, y, dot_out);
+  }
+}
+// A22_aug = A2 + gamma_2 M invW M (elliptic_interface.cc:810)
+static void apply_aug22(fdal_ctx *c, const double *x, double *y, double *dot_out) {
+  const DevCsr &M = c->dmat[FDAL_MAT_M];
+  if (c->cfg.winv_mode == FDAL_WINV_DIAG) {
+    spmv(c, M, x, EpiCouple{c->t_m0, c->d_winv, c->cfg.gamma2, nullptr, nullptr});
+  } else {
+    spmv(c, M, x, EpiAssign{c->t_m1, 1.0});
+    apply_winv_scaled(c, c->cfg.gamma2, c->t_m1, c->t_m0);
+  }
+  if (dot_out)
+    spmv2(c, c->dmat[FDAL_MAT_A2], x, M, c->t_m0, EpiDotX{y, x}, dot_out);
+  else
+    spmv2(c, c->dmat[FDAL_MAT_A2], x, M, c->t_m0, EpiAssign{y, 1.0});
+}
+static void apply_aug(fdal_ctx *c, int which, const double *x, double *y, double *dot_out) {
+  if (which == FDAL_AMG_A11)
+    apply_aug11(c, x, y, dot_out);
+  else
+    apply_aug22(c, x, y, dot_out);
+}
+
+// elliptic 2x2 augmented block [[A11g,A12g],[A21g,A22g]] applied to [x0;x1]:
+//   w = C x0 - M x1 ; tw = invW w ; y0 = A1 x0 + g1 Ct tw ; y1 = A2 x1 - g2 M tw
+// (the four LinearOperator blocks of elliptic_interface.cc:807-813 share tw)
+static void elliptic_w(fdal_ctx *c, const double *x0, const double *x1, double *w) {
+  spmv(c, c->dmat[FDAL_MAT_C], x0, EpiAssign{w, 1.0});
+  spmv(c, c->dmat[FDAL_MAT_M], x1, EpiAdd{w, -1.0});
+}
+static void apply_aug_block(fdal_ctx *c, const double *x, double *y, double *dot_out) {
+  const double *x0 = x, *x1 = x + c->n0;
+  double *y0 = y, *y1 = y + c->n0;
+  elliptic_w(c, x0, x1, c->t_m1);
+  apply_winv_scaled(c, 1.0, c->t_m1, c->t_m2);  // tw (exact modes use t_m2 internally: see below)
+  axpby(c, c->m, c->cfg.gamma, c->t_m2, 0.0, c->t_m0);
+  spmv2(c, c->dmat[FDAL_MAT_A], x0, c->dmat[FDAL_MAT_CT], c->t_m0, EpiAssign{y0, 1.0});
+  axpby(c, c->m, -c->cfg.gamma2, c->t_m2, 0.0, c->t_m0);
+  spmv2(c, c->dmat[FDAL_MAT_A2], x1, c->dmat[FDAL_MAT_M], c->t_m0, EpiAssign{y1, 1.0});
+  if (dot_out) dot(c, c->n0 + c->n1, x, y, dot_out);
+}
+
+// AA.vmult / system_operator.vmult (a7)
+static void apply_system(fdal_ctx *c, const double *x, double *y) {
+  const double *x0 = x, *x1 = x + c->n0, *x2 = x + c->n0 + c->n1;
+  double *y0 = y, *y1 = y + c->n0, *y2 = y + c->n0 + c->n1;
+  const DevCsr &A = c->dmat[FDAL_MAT_A], &Ct = c->dmat[FDAL_MAT_CT];
+  switch (c->cfg.kind) {
+    case FDAL_KIND_LAPLACE:
+      // y0 = A x0 + Ct (gamma invW C x0 + x1) ; y1 = C x0
+      if (c->cfg.aug_explicit) {
+        spmv(c, c->dmat[FDAL_MAT_C], x0, EpiAssign{y1, 1.0});
+        spmv2(c, A, x0, Ct, x1, EpiAssign{y0, 1.0});
+      } else {
+        couple_phase1(c, x0, c->cfg.gamma, x1, y1, c->t_m0);
+        spmv2(c, A, x0, Ct, c->t_m0, EpiAssign{y0, 1.0});
+      }
+      break;
+    case FDAL_KIND_STOKES:
+    case FDAL_KIND_STOKES_DIAG_MINRES:
+      if (c->cfg.aug_explicit) {
+        spmv(c, c->dmat[FDAL_MAT_C], x0, EpiAssign{y2, 1.0});
+        spmv2(c, A, x0, Ct, x2, EpiAssign{y0, 1.0});
+      } else {
+        couple_phase1(c, x0, c->cfg.gamma, x2, y2, c->t_m0);
+        spmv2(c, A, x0, Ct, c->t_m0, EpiAssign{y0, 1.0});
+      }
+      spmv(c, c->dmat[FDAL_MAT_BT], x1, EpiAdd{y0, 1.0});
+      spmv(c, c->dmat[FDAL_MAT_B], x0, EpiAssign{y1, 1.0});
+      if (c->cfg.grad_div_in_operator) {
+        apply_mp_inv(c, y1, c->t_p1);
+        spmv(c, c->dmat[FDAL_MAT_BT], c->t_p1, EpiAdd{y0, c->cfg.gamma_grad_div});
+      }
+      break;
+    default: {
+      // w = C x0 - M x1 ; tw = invW w
+      // y0 = A1 x0 + Ct (g1 tw + x2) ; y1 = A2 x1 - M (g2 tw + x2) ; y2 = w
+      elliptic_w(c, x0, x1, y2);
+      apply_winv_scaled(c, 1.0, y2, c->t_m2);
+      axpby(c, c->m, 1.0, x2, 0.0, c->t_m0);
+      axpby(c, c->m, c->cfg.gamma, c->t_m2, 1.0, c->t_m0);
+      spmv2(c, A, x0, Ct, c->t_m0, EpiAssign{y0, 1.0});
+      axpby(c, c->m, -1.0, x2, 0.0, c->t_m0);
+      axpby(c, c->m, -c->cfg.gamma2, c->t_m2, 1.0, c->t_m0);
+      spmv2(c, c->dmat[FDAL_MAT_A2], x1, c->dmat[FDAL_MAT_M], c->t_m0, EpiAssign{y1, 1.0});
+    } break;
+  }
+}
+
+// Aug_inv = inverse_operator(Aug, SolverCG, AMG) (a8)
+static int apply_aug_inv(fdal_ctx *c, int which, const double *b, double *x, int *its) {
+  CgWs &w = which == FDAL_AMG_A11 ? c->cg11 : c->cg22;
+  OpFn op = [c, which](const double *in, double *out, double *d) { apply_aug(c, which, in, out, d); };
+  OpFn pr;
+  if (c->cfg.inner_prec == FDAL_PREC_AMG)
+    pr = [c, which](const double *r, double *z, double *d) { vcycle(c, c->amg[which], r, z, d); };
+  else
+    pr = [c, &w](const double *r, double *z, double *d) {
+      dcopy(c, w.n, r, z);
+      dot(c, w.n, r, z, d);
+    };
+  int st = cg_solve(c, w, op, pr, c->cfg.inner, b, x, its, FDAL_ERR_INNER_NO_CONVERGENCE);
+  if (which == FDAL_AMG_A11)
+    c->its_a11 += *its;
+  else
+    c->its_a22 += *its;
+  c->n_inner_solves++;
+  if (st && !c->fail) c->fail = st;
+  return st;
+}
+
+// the five P.vmult (a1-a5)
+static int apply_prec(fdal_ctx *c, const double *u, double *v) {
+  const double *u0 = u, *u1 = u + c->n0, *u2 = u + c->n0 + c->n1;
+  double *v0 = v, *v1 = v + c->n0, *v2 = v + c->n0 + c->n1;
+  const double g = c->cfg.gamma;
+  const DevCsr &Ct = c->dmat[FDAL_MAT_CT];
+  int its = 0;
+  switch (c->cfg.kind) {
+    case FDAL_KIND_LAPLACE:
+      apply_winv_scaled(c, -g, u1, v1);
+      spmv(c, Ct, v1, EpiResid{c->t_n0, u0});
+      apply_aug_inv(c, FDAL_AMG_A11, c->t_n0, v0, &its);
+      break;
+    case FDAL_KIND_STOKES:
+      apply_winv_scaled(c, -g, u2, v2);
+      apply_mp_inv(c, u1, v1);
+      dscale(c, c->n1, -c->cfg.gamma_grad_div, v1);
+      spmv(c, c->dmat[FDAL_MAT_BT], v1, EpiResid{c->t_n0, u0});
+      spmv(c, Ct, v2, EpiAdd{c->t_n0, -1.0});
+      apply_aug_inv(c, FDAL_AMG_A11, c->t_n0, v0, &its);
+      break;
+    case FDAL_KIND_STOKES_DIAG_MINRES:
+      apply_winv_scaled(c, g, u2, v2);
+      apply_mp_inv(c, u1, v1);
+      dscale(c, c->n1, c->cfg.gamma_grad_div, v1);
+      apply_aug_inv(c, FDAL_AMG_A11, u0, v0, &its);
+      break;
+    case FDAL_KIND_ELLIPTIC_IDEAL: {
+      apply_winv_scaled(c, -g, u2, v2);
+      double *uu = c->t_N0;  // [n0 | n1]
+      spmv(c, Ct, v2, EpiResid{uu, u0});
+      dcopy(c, c->n1, u1, uu + c->n0);
+      spmv(c, c->dmat[FDAL_MAT_M], v2, EpiAdd{uu + c->n0, 1.0});
+      OpFn op = [c](const double *in, double *out, double *d) { apply_aug_block(c, in, out, d); };
+      OpFn pr;
+      if (c->cfg.inner_prec == FDAL_PREC_AMG)
+        pr = [c](const double *r, double *z, double *d) {
+          vcycle(c, c->amg[0], r, z, nullptr);
+          vcycle(c, c->amg[1], r + c->n0, z + c->n0, nullptr);
+          dot(c, c->n0 + c->n1, r, z, d);
+        };
+      else
+        pr = [c](const double *r, double *z, double *d) {
+          dcopy(c, c->n0 + c->n1, r, z);
+          dot(c, c->n0 + c->n1, r, z, d);
+        };
+      int st = cg_solve(c, c->cgblk, op, pr, c->cfg.inner, uu, v, &its, FDAL_ERR_INNER_NO_CONVERGENCE);
+      c->its_a11 += its;
+      c->n_inner_solves++;
+      if (st && !c->fail) c->fail = st;
+    } break;
+    case FDAL_KIND_ELLIPTIC_MODIFIED: {
+      apply_winv_scaled(c, -g, u2, v2);
+      // d1 = A22inv (u2 + M d2)
+      dcopy(c, c->n1, u1, c->t_p0);
+      spmv(c, c->dmat[FDAL_MAT_M], v2, EpiAdd{c->t_p0, 1.0});
+      apply_aug_inv(c, FDAL_AMG_A22, c->t_p0, v1, &its);
+      // d0 = A11inv (u + gamma Ct invW M d1 - Ct d2) = A11inv (u + Ct (gamma invW M d1 - d2))
+      spmv(c, c->dmat[FDAL_MAT_M], v1, EpiAssign{c->t_m1, 1.0});
+      // t = d2 - gamma invW M d1  =>  u0 - Ct t is the bracket above
+      apply_winv_scaled(c, -g, c->t_m1, c->t_m0);
+      axpby(c, c->m, 1.0, v2, 1.0, c->t_m0);
+      spmv(c, Ct, c->t_m0, EpiResid{c->t_n0, u0});
+      apply_aug_inv(c, FDAL_AMG_A11, c->t_n0, v0, &its);
+    } break;
+  }
+  return c->fail;
+}
+
+}  // namespace fdal
+
+// ====================================================================== outer solvers
+namespace fdal {
+
+static void record(fdal_solve_info *info, double res) {
+  if (info->n_history < FDAL_MAX_HISTORY) info->residual_history[info->n_history++] = res;
+}
+
+// SolverFGMRES (a12): batched classical Gram-Schmidt with one
+// re-orthogonalisation pass; Hessenberg / Givens on the host (O(restart^2)).
+static int fgmres(fdal_ctx *c, const double *b, double *x, fdal_solve_info *info) {
+  const int64_t N = c->N;
+  const int mb = c->cfg.restart;
+  std::vector<double> H((size_t)(mb + 1) * mb, 0.0), g(mb + 1), cs(mb), sn(mb), y(mb), hh(2 * (mb + 2));
+  ControlState ctl;
+  ctl.c = c->cfg.outer;
+  int acc = 0, state = ST_ITERATE, st;
+  auto Vj = [&](int j) { return c->V + (size_t)j * N; };
+  auto Zj = [&](int j) { return c->Z + (size_t)j * N; };
+  do {
+    apply_system(c, x, Vj(0));
+    axpby(c, N, 1.0, b, -1.0, Vj(0));
+    dot(c, N, Vj(0), Vj(0), c->d_scal);
+    double rr;
+    if ((st = read_scalars(c, c->d_scal, 1, &rr))) return st;
+    double res = std::sqrt(rr);
+    if (acc == 0) {
+      info->initial_residual = res;
+      record(info, res);
+    }
+    state = control_check(ctl, acc, res);
+    if (state != ST_ITERATE) break;
+    k_scale_by_inv<<<grid_elems(c, N), kBlock, 0, c->stream>>>(N, Vj(0), c->d_scal, 1, Vj(0));
+    c->launches++;
+    std::fill(g.begin(), g.end(), 0.0);
+    g[0] = res;
+    int j = 0;
+    for (; j < mb && state == ST_ITERATE; ++j) {
+      apply_prec(c, Vj(j), Zj(j));
+      if (c->fail) break;
+      double *w = Vj(j + 1);
+      apply_system(c, Zj(j), w);
+      const int nv = j + 1;
+      double *h1 = c->d_h, *h2 = c->d_h + (mb + 2);
+      const int gd = grid_elems(c, N);
+      k_multidot<<<gd, kBlock, 0, c->stream>>>(N, N, w, c->V, N, nv, 0, reducer(c, h1));
+      k_multiaxpy<<<gd, kBlock, 0, c->stream>>>(N, w, c->V, N, nv, h1, -1.0);
+      k_multidot<<<gd, kBlock, 0, c->stream>>>(N, N, w, c->V, N, nv, 0, reducer(c, h2));
+      k_multiaxpy<<<gd, kBlock, 0, c->stream>>>(N, w, c->V, N, nv, h2, -1.0);
+      dot(c, N, w, w, h2 + nv);
+      k_scale_by_inv<<<gd, kBlock, 0, c->stream>>>(N, w, h2 + nv, 1, w);
+      c->launches += 5;
+      // one read-back per outer iteration: h1[0..nv), h2[0..nv], |w|^2
+      CU(cudaMemcpyAsync(c->h_scal, c->d_h, (size_t)(2 * (mb + 2)) * sizeof(double), cudaMemcpyDeviceToHost,
+                         c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+      double *h = &H[(size_t)j * (mb + 1)];
+      for (int i = 0; i < nv; ++i) h[i] = c->h_scal[i] + c->h_scal[(mb + 2) + i];
+      h[j + 1] = std::sqrt(c->h_scal[(mb + 2) + nv]);
+      for (int i = 0; i < j; ++i) {
+        const double t = cs[i] * h[i] + sn[i] * h[i + 1];
+        h[i + 1] = -sn[i] * h[i] + cs[i] * h[i + 1];
+        h[i] = t;
+      }
+      const double den = std::hypot(h[j], h[j + 1]);
+      cs[j] = h[j] / den;
+      sn[j] = h[j + 1] / den;
+      h[j] = den;
+      h[j + 1] = 0.0;
+      g[j + 1] = -sn[j] * g[j];
+      g[j] = cs[j] * g[j];
+      res = std::fabs(g[j + 1]);
+      ++acc;
+      record(info, res);
+      state = control_check(ctl, acc, res);
+    }
+    if (c->fail) state = ST_FAILURE;
+    const int k = j;
+    for (int i = k - 1; i >= 0; --i) {
+      double s = g[i];
+      for (int l = i + 1; l < k; ++l) s -= H[(size_t)l * (mb + 1) + i] * y[l];
+      y[i] = s / H[(size_t)i * (mb + 1) + i];
+    }
+    if (k > 0) {
+      CU(cudaMemcpyAsync(c->d_y, y.data(), (size_t)k * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+      k_multiaxpy<<<grid_elems(c, N), kBlock, 0, c->stream>>>(N, x, c->Z, N, k, c->d_y, 1.0);
+      c->launches++;
+      CU(cudaStreamSynchronize(c->stream));  // y is reused by the next cycle
+    }
+    if (c->fail) break;
+  } while (state == ST_ITERATE);
+  info->outer_iterations = ctl.last_step;
+  info->final_residual = ctl.last_value;
+  if (c->fail) return c->fail;
+  return state == ST_SUCCESS ? FDAL_OK : FDAL_ERR_OUTER_NO_CONVERGENCE;
+}
+
+// SolverMinRes (a13)
+static int minres(fdal_ctx *c, const double *b, double *x, fdal_solve_info *info) {
+  const int64_t N = c->N;
+  double *u[3] = {c->mr_u[0], c->mr_u[1], c->mr_u[2]}, *m[3] = {c->mr_m[0], c->mr_m[1], c->mr_m[2]}, *v = c->mr_v;
+  double delta[3] = {0, 0, 0}, f[2] = {0, 0}, e[2] = {0, 0};
+  double r_l2, r0, tau = 0, cc = 0, s = 0, d_ = 0;
+  ControlState ctl;
+  ctl.c = c->cfg.outer;
+  int j = 1, st;
+  auto hdot = [&](const double *a, const double *bb, double *out) -> int {
+    dot(c, N, a, bb, c->d_scal);
+    return read_scalars(c, c->d_scal, 1, out);
+  };
+  apply_system(c, x, m[0]);
+  dcopy(c, N, b, u[1]);
+  axpby(c, N, -1.0, m[0], 1.0, u[1]);
+  apply_prec(c, u[1], v);
+  if ((st = hdot(v, u[1], &delta[1]))) return st;
+  r0 = std::sqrt(std::fabs(delta[1]));
+  r_l2 = r0;
+  dzero(c, N, u[0]);
+  dzero(c, N, u[2]);
+  for (int i = 0; i < 3; ++i) dzero(c, N, m[i]);
+  info->initial_residual = r_l2;
+  record(info, r_l2);
+  int state = control_check(ctl, 0, r_l2);
+  while (state == ST_ITERATE && !c->fail) {
+    if (delta[1] != 0)
+      dscale(c, N, 1.0 / std::sqrt(delta[1]), v);
+    else
+      dzero(c, N, v);
+    apply_system(c, v, u[2]);
+    if (j > 1) axpby(c, N, -std::sqrt(delta[1] / delta[0]), u[0], 1.0, u[2]);
+    double gamma;
+    if ((st = hdot(u[2], v, &gamma))) return st;
+    axpby(c, N, -gamma / std::sqrt(delta[1]), u[1], 1.0, u[2]);
+    dcopy(c, N, v, m[0]);
+    apply_prec(c, u[2], v);
+    if ((st = hdot(v, u[2], &delta[2]))) return st;
+    const double sd2 = std::sqrt(std::fabs(delta[2]));
+    if (j == 1) {
+      d_ = gamma;
+      e[1] = sd2;
+    }
+    if (j > 1) {
+      d_ = s * e[0] - cc * gamma;
+      e[0] = cc * e[0] + s * gamma;
+      f[1] = s * sd2;
+      e[1] = -cc * sd2;
+    }
+    const double d = std::sqrt(d_ * d_ + std::fabs(delta[2]));
+    if (j > 1) tau *= s / cc;
+    cc = d_ / d;
+    tau *= cc;
+    s = sd2 / d;
+    if (j == 1) tau = r0 * cc;
+    axpby(c, N, -e[0], m[1], 1.0, m[0]);
+    if (j > 1) axpby(c, N, -f[0], m[2], 1.0, m[0]);
+    dscale(c, N, 1.0 / d, m[0]);
+    axpby(c, N, tau, m[0], 1.0, x);
+    r_l2 *= std::fabs(s);
+    record(info, r_l2);
+    state = control_check(ctl, j, r_l2);
+    ++j;
+    std::swap(m[2], m[1]);
+    std::swap(m[1], m[0]);
+    std::swap(u[0], u[1]);
+    std::swap(u[1], u[2]);
+    delta[0] = delta[1];
+    delta[1] = delta[2];
+    f[0] = f[1];
+    e[0] = e[1];
+  }
+  info->outer_iterations = ctl.last_step;
+  info->final_residual = ctl.last_value;
+  if (c->fail) return c->fail;
+  return state == ST_SUCCESS ? FDAL_OK : FDAL_ERR_OUTER_NO_CONVERGENCE;
+}
+
+// ------------------------------------------------------------------ finalize helpers
+static int invert_coarse(fdal_ctx *c, Amg &g) {
+  AmgLevel &C = g.lev.back();
+  const int n = C.n;
+  double *aug = nullptr, *col = nullptr, *pval = nullptr;
+  int *prow = nullptr, *sing = nullptr;
+  int st;
+  if ((st = dvec(c, &aug, (int64_t)n * 2 * n))) return st;
+  if ((st = dvec(c, &col, n))) return st;
+  if ((st = dvec(c, &pval, 1))) return st;
+  if ((st = dmalloc(c, &prow, 1))) return st;
+  if ((st = dmalloc(c, &sing, 1))) return st;
+  if ((st = dmalloc(c, &g.cinv, (size_t)n * n))) return st;
+  CU(cudaMemsetAsync(sing, 0, sizeof(int), c->stream));
+  const int tb = 256;
+  k_dense_from_csr<<<(n + tb - 1) / tb, tb, 0, c->stream>>>(n, C.A.rp, C.A.ci, C.A.v, aug);
+  const int gc = (2 * n + tb - 1) / tb;
+  for (int k = 0; k < n; ++k) {
+    k_gj_pivot<<<1, kBlock, 0, c->stream>>>(n, k, aug, prow, pval, sing);
+    k_gj_swap_scale<<<gc, tb, 0, c->stream>>>(n, k, aug, prow, pval);
+    k_gj_save_col<<<(n + tb - 1) / tb, tb, 0, c->stream>>>(n, k, aug, col);
+    k_gj_eliminate<<<dim3(gc, n), tb, 0, c->stream>>>(n, k, aug, col);
+  }
+  k_gj_extract<<<dim3((n + tb - 1) / tb, n), tb, 0, c->stream>>>(n, aug, g.cinv);
+  int hs = 0;
+  CU(cudaMemcpyAsync(&hs, sing, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  if (hs) {
+    set_err(c, "coarsest AMG operator is singular");
+    return FDAL_ERR_INVALID;
+  }
+  // the 2n^2 scratch is the largest setup allocation: release it now
+  cudaFree(aug);
+  c->allocs.erase(std::find(c->allocs.begin(), c->allocs.end(), (void *)aug));
+  return FDAL_OK;
+}
+
+static int prepare_amg(fdal_ctx *c, Amg &g) {
+  int st;
+  const int nl = (int)g.lev.size();
+  for (int l = 0; l < nl; ++l) {
+    AmgLevel &L = g.lev[l];
+    if (!L.hA.set) {
+      set_err(c, "AMG level %d was never set", l);
+      return FDAL_ERR_STATE;
+    }
+    L.n = (int)L.hA.nr;
+    if ((st = upload_csr(c, L.hA, L.A))) return st;
+    if (l < nl - 1) {
+      if (!L.hP.set) {
+        set_err(c, "AMG level %d has no prolongator", l);
+        return FDAL_ERR_STATE;
+      }
+      if (L.hP.nc != g.lev[l + 1].hA.nr) {
+        set_err(c, "AMG level %d: P has %lld columns, next level has %lld rows", l, (long long)L.hP.nc,
+                (long long)g.lev[l + 1].hA.nr);
+        return FDAL_ERR_SHAPE;
+      }
+      if ((st = upload_csr(c, L.hP, L.P))) return st;
+      if (!L.hR.set) host_transpose(L.hP, L.hR);
+      if ((st = upload_csr(c, L.hR, L.R))) return st;
+      if ((st = dvec(c, &L.invd, L.n))) return st;
+      if (!L.h_invd.empty()) {
+        CU(cudaMemcpyAsync(L.invd, L.h_invd.data(), (size_t)L.n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+      } else {
+        k_inv_diag_from_csr<<<(L.n + 255) / 256, 256, 0, c->stream>>>(L.n, L.A.rp, L.A.ci, L.A.v, L.invd);
+      }
+      if ((st = dvec(c, &L.r, L.n))) return st;
+      if ((st = dvec(c, &L.d, L.n))) return st;
+    }
+    if ((st = dvec(c, &L.xa, L.n))) return st;
+    if ((st = dvec(c, &L.xb, L.n))) return st;
+    if ((st = dvec(c, &L.b, L.n))) return st;
+    // host copies are no longer needed
+    L.hA = HostCsr();
+    L.hA.set = true;
+    L.hP.ci.clear(); L.hP.v.clear(); L.hP.rp.clear();
+    L.hR.ci.clear(); L.hR.v.clear(); L.hR.rp.clear();
+    L.hP.ci.shrink_to_fit(); L.hP.v.shrink_to_fit(); L.hR.ci.shrink_to_fit(); L.hR.v.shrink_to_fit();
+  }
+  if ((st = invert_coarse(c, g))) return st;
+  g.ready = true;
+  return FDAL_OK;
+}
+
+static int alloc_cg(fdal_ctx *c, CgWs &w, int64_t n) {
+  int st;
+  w.n = n;
+  if ((st = dvec(c, &w.r, n))) return st;
+  if ((st = dvec(c, &w.z, n))) return st;
+  if ((st = dvec(c, &w.p, n))) return st;
+  if ((st = dvec(c, &w.v, n))) return st;
+  if ((st = dvec(c, &w.scal, S_COUNT))) return st;
+  return FDAL_OK;
+}
+static int need(fdal_ctx *c, int id, const char *name) {
+  if (!c->hmat[id].set) {
+    set_err(c, "matrix %s not set", name);
+    return 0;
+  }
+  return 1;
+}
+static int invdiag_of(fdal_ctx *c, const DevCsr &M, double **out) {
+  int st = dvec(c, out, M.d.nrows);
+  if (st) return st;
+  k_inv_diag_from_csr<<<(M.d.nrows + 255) / 256, 256, 0, c->stream>>>(M.d.nrows, M.rp, M.ci, M.v, *out);
+  return FDAL_OK;
+}
+
+}  // namespace fdal
+
+// ====================================================================== C ABI
+#define CHECK_CTX(c) \
+  if (!(c)) return FDAL_ERR_INVALID
+#define NEED_FINAL(c)                              \
+  if (!(c)->finalized) {                           \
+    set_err((c), "call fdal_finalize first");      \
+    return FDAL_ERR_STATE;                         \
+  }
+
+extern "C" {
+
+const char *fdal_version(void) { return "fdal 0.1 (sm_100a CUDA, FP64)"; }
+
+int fdal_create(fdal_ctx **out, const fdal_config *cfg) {
+  if (!out || !cfg) return FDAL_ERR_INVALID;
+  if (cfg->kind < 0 || cfg->kind > FDAL_KIND_ELLIPTIC_MODIFIED) return FDAL_ERR_INVALID;
+  if (cfg->restart > 120) return FDAL_ERR_INVALID;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return FDAL_ERR_CUDA;  // no CPU fallback
+  if (cfg->device < 0 || cfg->device >= ndev) return FDAL_ERR_INVALID;
+  fdal_ctx *c = new (std::nothrow) fdal_ctx();
+  if (!c) return FDAL_ERR_ALLOC;
+  c->cfg = *cfg;
+  if (c->cfg.restart <= 0) c->cfg.restart = 30;
+  if (cudaSetDevice(cfg->device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete c;
+    return FDAL_ERR_CUDA;
+  }
+  cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, cfg->device);
+  *out = c;
+  return FDAL_OK;
+}
+
+void fdal_destroy(fdal_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->cfg.device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  for (void *p : c->allocs) cudaFree(p);
+  if (c->h_scal) cudaFreeHost(c->h_scal);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+const char *fdal_last_error(const fdal_ctx *c) { return c ? c->err.c_str() : "null context"; }
+
+int fdal_set_csr(fdal_ctx *c, int id, int64_t nr, int64_t nc, int64_t nnz, const int64_t *rp, const int32_t *ci,
+                 const double *v) {
+  CHECK_CTX(c);
+  if (id < 0 || id >= FDAL_MAT_COUNT || !rp || nr < 0 || nc < 0 || nnz < 0 || (nnz && (!ci || !v))) {
+    set_err(c, "fdal_set_csr: bad argument");
+    return FDAL_ERR_INVALID;
+  }
+  if (rp[0] != 0 || rp[nr] != nnz) {
+    set_err(c, "matrix %d: row_ptr inconsistent with nnz", id);
+    return FDAL_ERR_SHAPE;
+  }
+  if (nnz >= (int64_t)std::numeric_limits<int>::max()) {
+    set_err(c, "matrix %d: %lld nnz exceeds the 32-bit row_ptr of this build", id, (long long)nnz);
+    return FDAL_ERR_UNSUPPORTED;
+  }
+  HostCsr &h = c->hmat[id];
+  h.nr = nr;
+  h.nc = nc;
+  h.nnz = nnz;
+  h.rp.resize((size_t)nr + 1);
+  for (int64_t i = 0; i <= nr; ++i) {
+    if (i && rp[i] < rp[i - 1]) {
+      set_err(c, "matrix %d: row_ptr not monotone", id);
+      return FDAL_ERR_SHAPE;
+    }
+    h.rp[(size_t)i] = (int)rp[i];
+  }
+  h.ci.assign(ci, ci + nnz);
+  h.v.assign(v, v + nnz);
+  for (int64_t k = 0; k < nnz; ++k)
+    if (ci[k] < 0 || ci[k] >= nc) {
+      set_err(c, "matrix %d: column index out of range", id);
+      return FDAL_ERR_SHAPE;
+    }
+  h.set = true;
+  c->finalized = false;
+  return FDAL_OK;
+}
+
+int fdal_set_diag(fdal_ctx *c, int id, int64_t n, const double *d) {
+  CHECK_CTX(c);
+  if (!d || n < 0) return FDAL_ERR_INVALID;
+  if (id == FDAL_DIAG_W_INV)
+    c->h_winv.assign(d, d + n);
+  else if (id == FDAL_DIAG_MP_LUMPED_INV)
+    c->h_mp_lumped.assign(d, d + n);
+  else
+    return FDAL_ERR_INVALID;
+  c->finalized = false;
+  return FDAL_OK;
+}
+
+static void copy_view(const fdal_csr_view *v, HostCsr &h) {
+  h.nr = v->n_rows;
+  h.nc = v->n_cols;
+  h.nnz = v->nnz;
+  h.rp.resize((size_t)v->n_rows + 1);
+  for (int64_t i = 0; i <= v->n_rows; ++i) h.rp[(size_t)i] = (int)v->row_ptr[i];
+  h.ci.assign(v->col, v->col + v->nnz);
+  h.v.assign(v->val, v->val + v->nnz);
+  h.set = true;
+}
+int fdal_amg_set_level(fdal_ctx *c, int which, int level, const fdal_csr_view *A, const fdal_csr_view *P,
+                       const fdal_csr_view *R, const double *inv_diag, double lmax, int degree, double ratio) {
+  CHECK_CTX(c);
+  if (which < 0 || which > 1 || level < 0 || level > 30 || !A) return FDAL_ERR_INVALID;
+  if (A->nnz >= (int64_t)std::numeric_limits<int>::max()) return FDAL_ERR_UNSUPPORTED;
+  Amg &g = c->amg[which];
+  if (g.ready) {
+    set_err(c, "AMG hierarchy %d already finalized", which);
+    return FDAL_ERR_STATE;
+  }
+  if ((int)g.lev.size() < level + 1) g.lev.resize(level + 1);
+  AmgLevel &L = g.lev[level];
+  copy_view(A, L.hA);
+  if (P) {
+    if (P->n_rows != A->n_rows) {
+      set_err(c, "AMG level %d: P has %lld rows, A has %lld", level, (long long)P->n_rows, (long long)A->n_rows);
+      return FDAL_ERR_SHAPE;
+    }
+    copy_view(P, L.hP);
+  }
+  if (R) copy_view(R, L.hR);
+  L.h_invd.clear();
+  if (inv_diag) L.h_invd.assign(inv_diag, inv_diag + A->n_rows);
+  L.lmax = lmax;
+  L.degree = degree;
+  L.ratio = ratio;
+  c->finalized = false;
+  return FDAL_OK;
+}
+int fdal_amg_set_coarse(fdal_ctx *c, int which, int level, const fdal_csr_view *A) {
+  return fdal_amg_set_level(c, which, level, A, nullptr, nullptr, nullptr, 1.0, 0, 1.0);
+}
+
+int fdal_finalize(fdal_ctx *c) {
+  CHECK_CTX(c);
+  if (c->finalized) return FDAL_OK;
+  if (!c->allocs.empty()) {
+    set_err(c, "fdal_finalize may only be called once per context");
+    return FDAL_ERR_STATE;
+  }
+  CU(cudaSetDevice(c->cfg.device));
+  const int k = c->cfg.kind;
+  int st;
+  if (!need(c, FDAL_MAT_A, "A") || !need(c, FDAL_MAT_CT, "Ct")) return FDAL_ERR_STATE;
+  c->n0 = c->hmat[FDAL_MAT_A].nr;
+  c->m = c->hmat[FDAL_MAT_CT].nc;
+  if (c->hmat[FDAL_MAT_CT].nr != c->n0 || c->hmat[FDAL_MAT_A].nc != c->n0) {
+    set_err(c, "A must be n x n and Ct n x m");
+    return FDAL_ERR_SHAPE;
+  }
+  if (k == FDAL_KIND_LAPLACE) {
+    c->nblocks = 2;
+    c->n1 = c->m;
+    c->n2 = 0;
+  } else if (is_stokes(c)) {
+    if (!need(c, FDAL_MAT_BT, "Bt")) return FDAL_ERR_STATE;
+    if (c->hmat[FDAL_MAT_BT].nr != c->n0) {
+      set_err(c, "Bt must have n_u rows");
+      return FDAL_ERR_SHAPE;
+    }
+    c->nblocks = 3;
+    c->n1 = c->hmat[FDAL_MAT_BT].nc;
+    c->n2 = c->m;
+    if (!need(c, FDAL_MAT_MP, "Mp")) return FDAL_ERR_STATE;
+    if (c->hmat[FDAL_MAT_MP].nr != c->n1) return FDAL_ERR_SHAPE;
+  } else {
+    if (!need(c, FDAL_MAT_A2, "A2") || !need(c, FDAL_MAT_M, "M")) return FDAL_ERR_STATE;
+    if (c->hmat[FDAL_MAT_A2].nr != c->m || c->hmat[FDAL_MAT_M].nr != c->m) {
+      set_err(c, "A2 and M must be m x m");
+      return FDAL_ERR_SHAPE;
+    }
+    c->nblocks = 3;
+    c->n1 = c->m;
+    c->n2 = c->m;
+  }
+  c->N = c->n0 + c->n1 + c->n2;
+  if (c->cfg.winv_mode == FDAL_WINV_DIAG) {
+    if ((int64_t)c->h_winv.size() != c->m) {
+      set_err(c, "diagonal W^-1 of size m=%lld required", (long long)c->m);
+      return FDAL_ERR_STATE;
+    }
+  } else if (!need(c, FDAL_MAT_M, "M (exact W^-1)"))
+    return FDAL_ERR_STATE;
+
+  // reductions + scalars
+  if ((st = dmalloc(c, &c->d_partials, (size_t)kMaxPartials * 128))) return st;
+  if ((st = dmalloc(c, &c->d_counter, 4))) return st;
+  CU(cudaMemsetAsync(c->d_counter, 0, 4 * sizeof(unsigned int), c->stream));
+  if ((st = dvec(c, &c->d_scal, 512))) return st;
+  CU(cudaMallocHost((void **)&c->h_scal, 512 * sizeof(double)));
+
+  // explicit transposes (gather kernels only: no atomics, deterministic)
+  if (!c->hmat[FDAL_MAT_C].set) host_transpose(c->hmat[FDAL_MAT_CT], c->hmat[FDAL_MAT_C]);
+  if (is_stokes(c) && !c->hmat[FDAL_MAT_B].set) host_transpose(c->hmat[FDAL_MAT_BT], c->hmat[FDAL_MAT_B]);
+  for (int id = 0; id < FDAL_MAT_COUNT; ++id)
+    if (c->hmat[id].set) {
+      if ((st = upload_csr(c, c->hmat[id], c->dmat[id]))) return st;
+      // host copy no longer needed
+      HostCsr &h = c->hmat[id];
+      std::vector<int>().swap(h.ci);
+      std::vector<double>().swap(h.v);
+      std::vector<int>().swap(h.rp);
+    }
+  // Ct rides in the row pass of A (k_spmv2): same thread-per-row split
+  if (c->cfg.winv_mode == FDAL_WINV_DIAG) {
+    if ((st = dvec(c, &c->d_winv, c->m))) return st;
+    CU(cudaMemcpyAsync(c->d_winv, c->h_winv.data(), (size_t)c->m * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  }
+  // scratch
+  if ((st = dvec(c, &c->t_m0, c->m))) return st;
+  if ((st = dvec(c, &c->t_m1, c->m))) return st;
+  if ((st = dvec(c, &c->t_m2, c->m))) return st;
+  if ((st = dvec(c, &c->t_mw, c->m))) return st;
+  if ((st = dvec(c, &c->t_n0, c->n0))) return st;
+  if ((st = dvec(c, &c->t_p0, c->n1))) return st;
+  if ((st = dvec(c, &c->t_p1, c->n1))) return st;
+  if ((st = dvec(c, &c->t_N0, c->N))) return st;
+  if ((st = dvec(c, &c->t_N1, c->N))) return st;
+  if ((st = alloc_cg(c, c->cg11, c->n0))) return st;
+  if (is_elliptic(c)) {
+    if ((st = alloc_cg(c, c->cg22, c->n1))) return st;
+    if (k == FDAL_KIND_ELLIPTIC_IDEAL && (st = alloc_cg(c, c->cgblk, c->n0 + c->n1))) return st;
+  }
+  // mass solves
+  if (c->cfg.winv_mode != FDAL_WINV_DIAG) {
+    if ((st = alloc_cg(c, c->cgmass_m, c->m))) return st;
+    if ((st = invdiag_of(c, c->dmat[FDAL_MAT_M], &c->d_m_invdiag))) return st;
+    if ((st = mass_calibrate(c, c->cgmass_m, c->dmat[FDAL_MAT_M], c->d_m_invdiag, &c->mass_its_m))) return st;
+  }
+  if (is_stokes(c)) {
+    if ((st = alloc_cg(c, c->cgmass_p, c->n1))) return st;
+    if (c->cfg.mp_inv_mode == FDAL_MPINV_EXACT) {
+      if ((st = invdiag_of(c, c->dmat[FDAL_MAT_MP], &c->d_mp_invdiag))) return st;
+      if ((st = mass_calibrate(c, c->cgmass_p, c->dmat[FDAL_MAT_MP], c->d_mp_invdiag, &c->mass_its_p))) return st;
+    } else {
+      if ((st = dvec(c, &c->d_mp_lumped, c->n1))) return st;
+      if ((int64_t)c->h_mp_lumped.size() == c->n1) {
+        CU(cudaMemcpyAsync(c->d_mp_lumped, c->h_mp_lumped.data(), (size_t)c->n1 * sizeof(double),
+                           cudaMemcpyHostToDevice, c->stream));
+      } else {
+        // M_p * 1, inverted (stokes_immersed_boundary.cc:946-952)
+        k_fill<<<grid_elems(c, c->n1), kBlock, 0, c->stream>>>(c->n1, c->t_p0, 1.0);
+        spmv(c, c->dmat[FDAL_MAT_MP], c->t_p0, EpiAssign{c->d_mp_lumped, 1.0});
+        k_reciprocal<<<grid_elems(c, c->n1), kBlock, 0, c->stream>>>(c->n1, c->d_mp_lumped);
+      }
+    }
+  }
+  // AMG
+  if (c->cfg.inner_prec == FDAL_PREC_AMG) {
+    for (int a = 0; a < 2; ++a) {
+      if (a == 1 && !is_elliptic(c)) continue;
+      if (c->amg[a].lev.empty()) {
+        set_err(c, "AMG hierarchy %d not set", a);
+        return FDAL_ERR_STATE;
+      }
+      if (c->amg[a].lev[0].hA.nr != (a == 0 ? c->n0 : c->n1)) {
+        set_err(c, "AMG hierarchy %d: fine level has %lld rows, block has %lld", a,
+                (long long)c->amg[a].lev[0].hA.nr, (long long)(a == 0 ? c->n0 : c->n1));
+        return FDAL_ERR_SHAPE;
+      }
+      if ((st = prepare_amg(c, c->amg[a]))) return st;
+    }
+  }
+  // outer Krylov workspace
+  const int mb = c->cfg.restart;
+  if (k == FDAL_KIND_STOKES_DIAG_MINRES) {
+    for (int i = 0; i < 3; ++i) {
+      if ((st = dvec(c, &c->mr_u[i], c->N))) return st;
+      if ((st = dvec(c, &c->mr_m[i], c->N))) return st;
+    }
+    if ((st = dvec(c, &c->mr_v, c->N))) return st;
+  } else {
+    if ((st = dvec(c, &c->V, (int64_t)(mb + 1) * c->N))) return st;
+    if ((st = dvec(c, &c->Z, (int64_t)mb * c->N))) return st;
+  }
+  if ((st = dvec(c, &c->d_h, 2 * (mb + 2) + 8))) return st;
+  if ((st = dvec(c, &c->d_y, mb + 8))) return st;
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  c->finalized = true;
+  return FDAL_OK;
+}
+
+int fdal_block_sizes(const fdal_ctx *c, int64_t sizes[3], int *nb) {
+  CHECK_CTX(c);
+  sizes[0] = c->n0;
+  sizes[1] = c->n1;
+  sizes[2] = c->n2;
+  *nb = c->nblocks;
+  return FDAL_OK;
+}
+
+// ---- host-pointer wrappers: stage through t_N0 / t_N1 -----------------------------
+static int h2d(fdal_ctx *c, double *d, const double *h, int64_t n) {
+  CU(cudaMemcpyAsync(d, h, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  return FDAL_OK;
+}
+static int d2h(fdal_ctx *c, double *h, const double *d, int64_t n) {
+  CU(cudaMemcpyAsync(h, d, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  return FDAL_OK;
+}
+#define BEGIN_CALL(c)              \
+  CHECK_CTX(c);                    \
+  NEED_FINAL(c);                   \
+  CU(cudaSetDevice((c)->cfg.device)); \
+  (c)->fail = 0
+
+int fdal_spmv_dev(fdal_ctx *c, int id, int transpose, const double *d_x, double *d_y) {
+  BEGIN_CALL(c);
+  if (id < 0 || id >= FDAL_MAT_COUNT) return FDAL_ERR_INVALID;
+  int use = id;
+  if (transpose) {
+    if (id == FDAL_MAT_CT) use = FDAL_MAT_C;
+    else if (id == FDAL_MAT_C) use = FDAL_MAT_CT;
+    else if (id == FDAL_MAT_BT) use = FDAL_MAT_B;
+    else if (id == FDAL_MAT_B) use = FDAL_MAT_BT;
+    else if (id == FDAL_MAT_A || id == FDAL_MAT_A2 || id == FDAL_MAT_M || id == FDAL_MAT_MP) use = id;  // symmetric
+  }
+  if (!c->dmat[use].set) {
+    set_err(c, "matrix %d not available", use);
+    return FDAL_ERR_INVALID;
+  }
+  spmv(c, c->dmat[use], d_x, EpiAssign{d_y, 1.0});
+  CU(cudaStreamSynchronize(c->stream));
+  return FDAL_OK;
+}
+int fdal_spmv(fdal_ctx *c, int id, int transpose, const double *x, double *y) {
+  BEGIN_CALL(c);
+  if (id < 0 || id >= FDAL_MAT_COUNT || !c->dmat[id].set) return FDAL_ERR_INVALID;
+  const int64_t nin = transpose ? c->dmat[id].d.nrows : c->dmat[id].d.ncols;
+  const int64_t nout = transpose ? c->dmat[id].d.ncols : c->dmat[id].d.nrows;
+  int st;
+  if ((st = h2d(c, c->t_N0, x, nin))) return st;
+  if ((st = fdal_spmv_dev(c, id, transpose, c->t_N0, c->t_N1))) return st;
+  return d2h(c, y, c->t_N1, nout);
+}
+int fdal_apply_aug_dev(fdal_ctx *c, int which, const double *d_x, double *d_y) {
+  BEGIN_CALL(c);
+  if (which == FDAL_AMG_A22 && !is_elliptic(c)) return FDAL_ERR_INVALID;
+  apply_aug(c, which, d_x, d_y, nullptr);
+  CU(cudaStreamSynchronize(c->stream));
+  return c->fail;
+}
+int fdal_apply_aug(fdal_ctx *c, int which, const double *x, double *y) {
+  BEGIN_CALL(c);
+  const int64_t n = which == FDAL_AMG_A11 ? c->n0 : c->n1;
+  int st;
+  if ((st = h2d(c, c->t_N0, x, n))) return st;
+  if ((st = fdal_apply_aug_dev(c, which, c->t_N0, c->t_N1))) return st;
+  return d2h(c, y, c->t_N1, n);
+}
+int fdal_apply_system(fdal_ctx *c, const double *x, double *y) {
+  BEGIN_CALL(c);
+  int st;
+  if ((st = h2d(c, c->t_N0, x, c->N))) return st;
+  apply_system(c, c->t_N0, c->t_N1);
+  if ((st = d2h(c, y, c->t_N1, c->N))) return st;
+  return c->fail;
+}
+int fdal_apply_winv(fdal_ctx *c, const double *x, double *y) {
+  BEGIN_CALL(c);
+  int st;
+  if ((st = h2d(c, c->t_N0, x, c->m))) return st;
+  apply_winv_scaled(c, 1.0, c->t_N0, c->t_N1);
+  return d2h(c, y, c->t_N1, c->m);
+}
+int fdal_apply_mp_inv(fdal_ctx *c, const double *x, double *y, int *its) {
+  BEGIN_CALL(c);
+  if (!is_stokes(c)) return FDAL_ERR_INVALID;
+  int st;
+  c->its_mass = 0;
+  if ((st = h2d(c, c->t_N0, x, c->n1))) return st;
+  st = apply_mp_inv(c, c->t_N0, c->t_N1);
+  if (its) *its = c->its_mass;
+  if (st) return st;
+  return d2h(c, y, c->t_N1, c->n1);
+}
+int fdal_apply_amg_dev(fdal_ctx *c, int which, const double *d_r, double *d_z) {
+  BEGIN_CALL(c);
+  if (which < 0 || which > 1 || !c->amg[which].ready) return FDAL_ERR_STATE;
+  vcycle(c, c->amg[which], d_r, d_z, nullptr);
+  CU(cudaStreamSynchronize(c->stream));
+  return FDAL_OK;
+}
+int fdal_apply_amg(fdal_ctx *c, int which, const double *r, double *z) {
+  BEGIN_CALL(c);
+  if (which < 0 || which > 1 || !c->amg[which].ready) return FDAL_ERR_STATE;
+  const int64_t n = c->amg[which].lev[0].n;
+  int st;
+  if ((st = h2d(c, c->t_N0, r, n))) return st;
+  if ((st = fdal_apply_amg_dev(c, which, c->t_N0, c->t_N1))) return st;
+  return d2h(c, z, c->t_N1, n);
+}
+int fdal_apply_aug_inv(fdal_ctx *c, int which, const double *b, double *x, int *its) {
+  BEGIN_CALL(c);
+  if (which == FDAL_AMG_A22 && !is_elliptic(c)) return FDAL_ERR_INVALID;
+  const int64_t n = which == FDAL_AMG_A11 ? c->n0 : c->n1;
+  int st, i = 0;
+  if ((st = h2d(c, c->t_N0, b, n))) return st;
+  st = apply_aug_inv(c, which, c->t_N0, c->t_N1, &i);
+  if (its) *its = i;
+  if (st) {
+    set_err(c, "inner CG did not converge in %d steps (SolverControl::NoConvergence)", i);
+    return st;
+  }
+  return d2h(c, x, c->t_N1, n);
+}
+int fdal_apply_prec(fdal_ctx *c, const double *u, double *v, int inner_its[2]) {
+  BEGIN_CALL(c);
+  int st;
+  c->its_a11 = c->its_a22 = 0;
+  // apply_prec uses t_N0 (ideal variant): stage through V-independent buffers
+  double *du = c->t_N1, *dv = nullptr;
+  if ((st = dvec(c, &dv, c->N))) return st;
+  if ((st = h2d(c, du, u, c->N))) return st;
+  st = apply_prec(c, du, dv);
+  if (inner_its) {
+    inner_its[0] = c->its_a11;
+    inner_its[1] = c->its_a22;
+  }
+  int st2 = d2h(c, v, dv, c->N);
+  cudaFree(dv);
+  c->allocs.erase(std::find(c->allocs.begin(), c->allocs.end(), (void *)dv));
+  if (st) set_err(c, "inner solver did not converge (SolverControl::NoConvergence)");
+  return st ? st : st2;
+}
+int fdal_augment_rhs(fdal_ctx *c, double *rhs) {
+  BEGIN_CALL(c);
+  int st;
+  if ((st = h2d(c, c->t_N0, rhs, c->N))) return st;
+  double *g = c->t_N0 + c->n0 + (c->nblocks == 3 ? c->n1 : 0);
+  apply_winv_scaled(c, c->cfg.gamma, g, c->t_m0);
+  spmv(c, c->dmat[FDAL_MAT_CT], c->t_m0, EpiAdd{c->t_N0, 1.0});
+  return d2h(c, rhs, c->t_N0, c->N);
+}
+
+int fdal_solve_dev(fdal_ctx *c, const double *d_rhs, double *d_x, fdal_solve_info *info) {
+  BEGIN_CALL(c);
+  fdal_solve_info local;
+  if (!info) info = &local;
+  memset(info, 0, sizeof(*info));
+  c->its_a11 = c->its_a22 = c->its_mass = c->n_inner_solves = 0;
+  const int64_t l0 = c->launches;
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  CU(cudaEventRecord(e0, c->stream));
+  int st = c->cfg.kind == FDAL_KIND_STOKES_DIAG_MINRES ? minres(c, d_rhs, d_x, info) : fgmres(c, d_rhs, d_x, info);
+  cudaEventRecord(e1, c->stream);
+  cudaEventSynchronize(e1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  info->solve_ms = ms;
+  info->status = st;
+  info->inner_iterations = c->its_a11;
+  info->inner_iterations_a22 = c->its_a22;
+  info->inner_solves = c->n_inner_solves;
+  info->mass_iterations = c->its_mass;
+  info->kernel_launches = c->launches - l0;
+  if (st == FDAL_ERR_INNER_NO_CONVERGENCE)
+    set_err(c, "inner CG did not converge (SolverControl::NoConvergence)");
+  else if (st == FDAL_ERR_OUTER_NO_CONVERGENCE)
+    set_err(c, "outer solver did not converge after %d steps", info->outer_iterations);
+  else if (st == FDAL_ERR_MASS_NO_CONVERGENCE)
+    set_err(c, "pressure mass CG did not converge");
+  return st;
+}
+int fdal_solve(fdal_ctx *c, const double *rhs, double *x, fdal_solve_info *info) {
+  BEGIN_CALL(c);
+  int st;
+  double *drhs = c->t_N1, *dx = nullptr;
+  if ((st = dvec(c, &dx, c->N))) return st;
+  if ((st = h2d(c, drhs, rhs, c->N))) return st;
+  if ((st = h2d(c, dx, x, c->N))) return st;
+  st = fdal_solve_dev(c, drhs, dx, info);
+  int st2 = d2h(c, x, dx, c->N);
+  cudaFree(dx);
+  c->allocs.erase(std::find(c->allocs.begin(), c->allocs.end(), (void *)dx));
+  return st ? st : st2;
+}
+
+// ---- measurement ----------------------------------------------------------------------
+static double csr_bytes(const CsrDev &A) {
+  return 12.0 * (double)A.nnz + 4.0 * ((double)A.nrows + 1) + 8.0 * (double)A.ncols + 8.0 * (double)A.nrows;
+}
+int fdal_time_kernel(fdal_ctx *c, int what, int param, int warmup, int reps, int flush_l2, double *avg_ms,
+                     double *alg_bytes, int64_t *launches_per_rep) {
+  BEGIN_CALL(c);
+  int st;
+  if (flush_l2 && !c->flush_buf) {
+    c->flush_bytes = (size_t)256 << 20;
+    if ((st = dmalloc(c, &c->flush_buf, c->flush_bytes))) return st;
+  }
+  const DevCsr &A = c->dmat[FDAL_MAT_A];
+  double *x = c->t_N0, *y = c->t_N1;
+  k_fill<<<grid_elems(c, c->N), kBlock, 0, c->stream>>>(c->N, x, 1.0);
+  double bytes = 0;
+  std::function<void()> run;
+  const int64_t N = c->N, n0 = c->n0;
+  switch (what) {
+    case FDAL_TIME_SPMV_A:
+      run = [&]() { spmv(c, A, x, EpiAssign{y, 1.0}); };
+      bytes = csr_bytes(A.d);
+      break;
+    case FDAL_TIME_AUG:
+      run = [&]() { apply_aug11(c, x, y, nullptr); };
+      bytes = csr_bytes(A.d) + csr_bytes(c->dmat[FDAL_MAT_C].d) + 12.0 * (double)c->dmat[FDAL_MAT_CT].d.nnz +
+              4.0 * ((double)n0 + 1) + 16.0 * (double)c->m;
+      break;
+    case FDAL_TIME_VCYCLE: {
+      if (!c->amg[0].ready) return FDAL_ERR_STATE;
+      run = [&]() { vcycle(c, c->amg[0], x, y, nullptr); };
+      Amg &g = c->amg[0];
+      for (size_t l = 0; l + 1 < g.lev.size(); ++l) {
+        const AmgLevel &L = g.lev[l];
+        const double nl = (double)L.n;
+        const int deg = L.degree;
+        // pre: zero step (3 vec) + (deg-1) fused steps; residual; R; P; post: deg fused steps
+        bytes += 24.0 * nl + (2 * deg - 1) * (csr_bytes(L.A.d) + 32.0 * nl) + (csr_bytes(L.A.d) + 8.0 * nl) +
+                 csr_bytes(L.R.d) + csr_bytes(L.P.d) + 8.0 * nl;
+      }
+      const double cn = (double)g.lev.back().n;
+      bytes += 8.0 * cn * cn + 16.0 * cn;
+    } break;
+    case FDAL_TIME_CHEB_FINE: {
+      if (!c->amg[0].ready || c->amg[0].lev.size() < 2) return FDAL_ERR_STATE;
+      AmgLevel &L = c->amg[0].lev[0];
+      run = [&]() {
+        EpiCheb<false> e{x, L.invd, L.xa, L.d, L.xb, 0.3, 0.7, 0};
+        spmv(c, L.A, L.xa, e);
+      };
+      bytes = csr_bytes(L.A.d) + 32.0 * (double)L.n;
+    } break;
+    case FDAL_TIME_DOT:
+      run = [&]() { dot(c, N, x, y, c->d_scal); };
+      bytes = 16.0 * (double)N;
+      break;
+    case FDAL_TIME_MULTIDOT: {
+      if (!c->V) return FDAL_ERR_STATE;
+      const int nv = std::max(1, std::min(param, c->cfg.restart));
+      run = [&, nv]() {
+        k_multidot<<<grid_elems(c, N), kBlock, 0, c->stream>>>(N, N, x, c->V, N, nv, 0, reducer(c, c->d_h));
+        c->launches++;
+      };
+      bytes = 8.0 * (double)N * (nv + (nv + kMultiDotGroup - 1) / kMultiDotGroup);
+    } break;
+    case FDAL_TIME_AXPY:
+      run = [&]() { axpby(c, N, 0.5, x, 1.0, y); };
+      bytes = 24.0 * (double)N;
+      break;
+    default:
+      return FDAL_ERR_INVALID;
+  }
+  for (int i = 0; i < warmup; ++i) run();
+  CU(cudaStreamSynchronize(c->stream));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  double total = 0;
+  const int64_t l0 = c->launches;
+  for (int i = 0; i < reps; ++i) {
+    if (flush_l2) CU(cudaMemsetAsync(c->flush_buf, i & 0xff, c->flush_bytes, c->stream));
+    CU(cudaEventRecord(e0, c->stream));
+    run();
+    CU(cudaEventRecord(e1, c->stream));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    total += ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  CU(cudaGetLastError());
+  if (avg_ms) *avg_ms = total / std::max(1, reps);
+  if (alg_bytes) *alg_bytes = bytes;
+  if (launches_per_rep) *launches_per_rep = (c->launches - l0) / std::max(1, reps);
+  return FDAL_OK;
+}
+
+// ---- multi-GPU entry points: filled in by comm.cu when built with NCCL ---------------------
+#ifndef FDAL_WITH_NCCL
+int fdal_nccl_unique_id(char id_out[128]) {
+  (void)id_out;
+  return FDAL_ERR_UNSUPPORTED;
+}
+int fdal_comm_init(fdal_ctx *c, const char id[128], int rank, int n_ranks) {
+  (void)id;
+  (void)rank;
+  (void)n_ranks;
+  CHECK_CTX(c);
+  set_err(c, "built without NCCL");
+  return FDAL_ERR_UNSUPPORTED;
+}
+int fdal_set_halo(fdal_ctx *c, int matrix_id, int level, int which, int64_t n_owned_cols, int64_t n_halo,
+                  const int32_t *send_counts, const int32_t *send_idx, const int32_t *recv_counts) {
+  (void)matrix_id; (void)level; (void)which; (void)n_owned_cols; (void)n_halo; (void)send_counts; (void)send_idx; (void)recv_counts;
+  CHECK_CTX(c);
+  set_err(c, "built without NCCL");
+  return FDAL_ERR_UNSUPPORTED;
+}
+#endif
+
+}  // extern "C"

@@ -1,0 +1,458 @@
+// kernels.cuh — hand-written sm_100a kernels of the AL solve path.
+//
+// Everything here is FP64 on CUDA cores and HBM-bound (arithmetic intensity of a
+// CSR SpMV is ~0.17 flop/B), so the design rules are: coalesced streaming of the
+// matrix arrays, x gathered through the read-only path (the whole x vector of the
+// largest configuration fits the 126 MB L2), epilogues fused into the row pass so
+// no intermediate vector goes back to HBM, reductions finished in-kernel
+// (last-block pattern, fixed summation order => run-to-run deterministic), and
+// grids sized as a multiple of the SM count with grid-stride loops.
+//
+// Reference call sites these kernels replace: K1 SparseMatrix::vmult,
+// K2 coupling_matrix.Tvmult/vmult, K3 the LinearOperator expression
+// `K + gamma * Ct * invW * C` (immersed_laplace.cc:884), K4 DiagonalMatrix::vmult,
+// K8 PreconditionAMG::vmult (Chebyshev steps, residual, restriction, prolongation),
+// K9/K10/K11 the Vector BLAS-1 inside SolverCG / SolverFGMRES.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fdal {
+
+constexpr int kBlock = 256;       // threads per CTA for every kernel here
+constexpr int kMaxGridPerSM = 8;  // CTAs per SM used to size grid-stride grids
+constexpr int kMaxPartials = 148 * 16;
+constexpr int kMultiDotGroup = 8;  // basis vectors accumulated per pass in V^T w
+
+struct CsrDev {
+  int nrows = 0, ncols = 0;
+  long long nnz = 0;
+  const int *rp = nullptr;
+  const int *ci = nullptr;
+  const double *v = nullptr;
+  int tpr = 8;  // threads per row
+};
+
+// x vector with an optional halo part (multi-GPU): columns [0,n_owned) are local,
+// [n_owned, ...) index the halo receive buffer of the matrix.
+struct XVec {
+  const double *x;
+  const double *halo;
+  int n_owned;
+};
+__device__ __forceinline__ double xload(const XVec &X, int c) {
+  return c < X.n_owned ? __ldg(X.x + c) : __ldg(X.halo + (c - X.n_owned));
+}
+
+// ---- in-kernel reduction: block partial -> last block sums partials in fixed order
+struct Reducer {
+  double *partials;       // [gridDim.x * n_out]
+  unsigned int *counter;  // self-resetting (atomicInc wrap)
+  double *out;            // [n_out] device scalars
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+// returns the block total in thread 0
+__device__ __forceinline__ double block_sum(double v, double *smem /*[32]*/) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();  // protect smem reuse
+  if (lane == 0) smem[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    v = lane < (blockDim.x >> 5) ? smem[lane] : 0.0;
+    v = warp_sum(v);
+  }
+  return v;
+}
+// Every thread of every block must call this, once per slot and in slot order.
+// Deterministic: the final summation order depends only on gridDim.x and
+// blockDim.x.  Returns true (for all threads of the block) in the one block that
+// finished the reduction, after R.out[] has been written.
+__device__ __forceinline__ bool reduce_finalize(double v, const Reducer &R, int slot, int n_out, double *smem) {
+  const double tot = block_sum(v, smem);
+  if (threadIdx.x == 0) R.partials[(size_t)blockIdx.x * n_out + slot] = tot;
+  if (slot != n_out - 1) return false;
+  // last slot of this block: publish all its partials and elect the last block
+  __shared__ bool s_last;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int t = atomicInc(R.counter, gridDim.x - 1);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  const bool last = s_last;
+  if (last) {
+    __threadfence();
+    for (int o = 0; o < n_out; ++o) {
+      double a = 0.0;
+      for (int b = threadIdx.x; b < gridDim.x; b += blockDim.x) a += R.partials[(size_t)b * n_out + o];
+      a = block_sum(a, smem);
+      if (threadIdx.x == 0) R.out[o] = a;
+    }
+  }
+  return last;
+}
+
+// ---- SpMV epilogues: called by the first lane of the row group with the row sum.
+// operator() returns the row's contribution to a fused reduction (0 if none).
+struct EpiAssign {  // y = alpha * A x
+  double *y;
+  double alpha;
+  static constexpr bool kReduce = false;
+  __device__ double operator()(int i, double s) const {
+    y[i] = alpha * s;
+    return 0.0;
+  }
+};
+struct EpiAdd {  // y += alpha * A x
+  double *y;
+  double alpha;
+  static constexpr bool kReduce = false;
+  __device__ double operator()(int i, double s) const {
+    y[i] += alpha * s;
+    return 0.0;
+  }
+};
+struct EpiResid {  // y = b - A x     (also u0 - Ct v1 in the preconditioners)
+  double *y;
+  const double *b;
+  static constexpr bool kReduce = false;
+  __device__ double operator()(int i, double s) const {
+    y[i] = b[i] - s;
+    return 0.0;
+  }
+};
+// phase 1 of the augmented operator on the C rows (m of them):
+//   w = C x (+ sub: w -= sub[i]) ; y1 = w (optional) ; t = a * winv .* w + add (optional)
+// winv == nullptr -> t = a * w + add (exact mass inverse applied afterwards)
+struct EpiCouple {
+  double *t;
+  const double *winv;
+  double a;
+  const double *add;
+  double *y1;
+  static constexpr bool kReduce = false;
+  __device__ double operator()(int i, double s) const {
+    if (y1) y1[i] = s;
+    double tv = a * (winv ? winv[i] * s : s);
+    if (add) tv += add[i];
+    t[i] = tv;
+    return 0.0;
+  }
+};
+struct EpiDotX {  // y = A x ; reduce x_i * y_i  (p.Ap of CG)
+  double *y;
+  const double *x;
+  static constexpr bool kReduce = true;
+  __device__ double operator()(int i, double s) const {
+    y[i] = s;
+    return x[i] * s;
+  }
+};
+// fused Chebyshev step: r = b - A x ; d = c1 d + c2 D^-1 r ; xout = xin + d
+template <bool REDUCE>
+struct EpiCheb {
+  const double *b, *invd, *xin;
+  double *d, *xout;
+  double c1, c2;
+  int first;  // 1: d is not read (c1 term absent)
+  static constexpr bool kReduce = REDUCE;
+  __device__ double operator()(int i, double s) const {
+    const double bi = b[i];
+    const double r = bi - s;
+    double dn = c2 * invd[i] * r;
+    if (!first) dn += c1 * d[i];
+    d[i] = dn;
+    const double xo = xin[i] + dn;
+    xout[i] = xo;
+    return REDUCE ? bi * xo : 0.0;  // r.z of the enclosing CG when b is the CG residual
+  }
+};
+
+// ---- CSR SpMV, TPR threads per row, grid-stride over row chunks ----------------
+template <int TPR, class Epi>
+__global__ void __launch_bounds__(kBlock) k_spmv(CsrDev A, XVec X, Epi epi, Reducer R) {
+  __shared__ double smem[32];
+  constexpr int rows_per_block = kBlock / TPR;
+  const int lane = threadIdx.x & (TPR - 1);
+  const int local_row = threadIdx.x / TPR;
+  double contrib = 0.0;
+  for (long long base = (long long)blockIdx.x * rows_per_block; base < A.nrows;
+       base += (long long)gridDim.x * rows_per_block) {
+    const long long row = base + local_row;
+    double s = 0.0;
+    if (row < A.nrows) {
+      const int k0 = __ldg(A.rp + row), k1 = __ldg(A.rp + row + 1);
+      for (int k = k0 + lane; k < k1; k += TPR) s += __ldg(A.v + k) * xload(X, __ldg(A.ci + k));
+    }
+#pragma unroll
+    for (int o = TPR >> 1; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, TPR);
+    if (lane == 0 && row < A.nrows) contrib += epi((int)row, s);
+  }
+  if (Epi::kReduce) reduce_finalize(contrib, R, 0, 1, smem);
+}
+
+// ---- fused augmented apply, phase 2:  y = A x + Ct t   (+ fused x.y) -------------
+// Two CSR matrices with the same row partition are walked in one row pass, so A x
+// never goes to memory before the coupling term is added (K3).  t already carries
+// gamma * W^-1 C x (phase 1), and for the block system also + x1.
+template <int TPR, class Epi>
+__global__ void __launch_bounds__(kBlock) k_spmv2(CsrDev A, XVec X, CsrDev Ct, const double *__restrict__ t, Epi epi,
+                                                   Reducer R) {
+  __shared__ double smem[32];
+  constexpr int rows_per_block = kBlock / TPR;
+  const int lane = threadIdx.x & (TPR - 1);
+  const int local_row = threadIdx.x / TPR;
+  double contrib = 0.0;
+  for (long long base = (long long)blockIdx.x * rows_per_block; base < A.nrows;
+       base += (long long)gridDim.x * rows_per_block) {
+    const long long row = base + local_row;
+    double s = 0.0;
+    if (row < A.nrows) {
+      const int k0 = __ldg(A.rp + row), k1 = __ldg(A.rp + row + 1);
+      const int c0 = __ldg(Ct.rp + row), c1 = __ldg(Ct.rp + row + 1);
+      for (int k = k0 + lane; k < k1; k += TPR) s += __ldg(A.v + k) * xload(X, __ldg(A.ci + k));
+      for (int k = c0 + lane; k < c1; k += TPR) s += __ldg(Ct.v + k) * __ldg(t + __ldg(Ct.ci + k));
+    }
+#pragma unroll
+    for (int o = TPR >> 1; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, TPR);
+    if (lane == 0 && row < A.nrows) contrib += epi((int)row, s);
+  }
+  if (Epi::kReduce) reduce_finalize(contrib, R, 0, 1, smem);
+}
+
+// ---- dense GEMV for the coarsest AMG level: y = Ainv b (one warp per row) --------
+__global__ void __launch_bounds__(kBlock) k_gemv(int n, const double *__restrict__ Ainv, const double *__restrict__ b,
+                                                  double *__restrict__ y) {
+  const int warp = (blockIdx.x * kBlock + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n) return;
+  const double *row = Ainv + (size_t)warp * n;
+  double s = 0.0;
+  for (int k = lane; k < n; k += 32) s += __ldg(row + k) * __ldg(b + k);
+  s = warp_sum(s);
+  if (lane == 0) y[warp] = s;
+}
+
+// ---- Krylov vector kernels (K9-K11) ------------------------------------------------
+// device scalar slots of one CG instance
+enum { S_RHO = 0, S_RHO_OLD = 1, S_PV = 2, S_RR = 3, S_COUNT = 8 };
+
+__global__ void __launch_bounds__(kBlock) k_dot(long long n, const double *__restrict__ a, const double *__restrict__ b,
+                                                 Reducer R) {
+  __shared__ double smem[32];
+  double s = 0.0;
+  for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n; i += (long long)gridDim.x * kBlock)
+    s += a[i] * b[i];
+  reduce_finalize(s, R, 0, 1, smem);
+}
+// z = d .* r and r.z in one pass (Jacobi preconditioner of the mass-matrix CG)
+__global__ void __launch_bounds__(kBlock) k_diag_prec_dot(long long n, const double *__restrict__ d,
+                                                           const double *__restrict__ r, double *__restrict__ z,
+                                                           Reducer R) {
+  __shared__ double smem[32];
+  double s = 0.0;
+  for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n; i += (long long)gridDim.x * kBlock) {
+    const double zi = d[i] * r[i];
+    z[i] = zi;
+    s += zi * r[i];
+  }
+  reduce_finalize(s, R, 0, 1, smem);
+}
+// p = z + beta p, beta = rho / rho_old (rho_old = +inf on the first iteration => p = z)
+__global__ void __launch_bounds__(kBlock) k_cg_update_p(long long n, const double *__restrict__ z, double *__restrict__ p,
+                                                         const double *__restrict__ scal) {
+  const double rho = scal[S_RHO], rho_old = scal[S_RHO_OLD];
+  const double beta = isinf(rho_old) ? 0.0 : rho / rho_old;
+  for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n; i += (long long)gridDim.x * kBlock)
+    p[i] = z[i] + beta * p[i];
+}
+// x += alpha p ; r -= alpha v ; rr = r.r ; rho_old = rho      (alpha = rho / p.v)
+// guard: a zero denominator (exactly converged fixed-count mass solve) freezes the iterate
+__global__ void __launch_bounds__(kBlock) k_cg_update_xr(long long n, long long n_dot, const double *__restrict__ p,
+                                                          const double *__restrict__ v, double *__restrict__ x,
+                                                          double *__restrict__ r, double *scal, Reducer R) {
+  __shared__ double smem[32];
+  const double rho = scal[S_RHO], pv = scal[S_PV];
+  const double alpha = (pv != 0.0) ? rho / pv : 0.0;
+  double s = 0.0;
+  for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n; i += (long long)gridDim.x * kBlock) {
+    x[i] += alpha * p[i];
+    const double ri = r[i] - alpha * v[i];
+    r[i] = ri;
+    if (i < n_dot) s += ri * ri;
+  }
+  // the block that finishes the reduction also rotates rho: every block has read
+  // rho before it published its partial, so nobody can still observe the old value
+  const bool last = reduce_finalize(s, R, 0, 1, smem);
+  if (last && threadIdx.x == 0) scal[S_RHO_OLD] = rho;
+}
+__global__ void k_set_scalar(double *p, double v) { *p = v; }
+
+// y = a x + b y   (a, b host scalars; x may alias y only if a-term unused)
+__global__ void __launch_bounds__(kBlock) k_axpby(long long n, double a, const double *__restrict__ x, double b,
+                                                   double *__restrict__ y) {
+  for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n; i += (long long)gridDim.x * kBlock)
+    y[i] = a * x[i] + (b == 0.0 ? 0.0 : b * y[i]);
+}
+// y = a * d .* x  (DiagonalMatrix::vmult with a scale, K4)
+__global__ void __launch_bounds__(kBlock) k_diag_scale(long long n, double a, const double *__restrict__ d,
+                                                        const double *__restrict__ x, double *__restrict__ y) {
+  for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n; i += (long long)gridDim.x * kBlock)
+    y[i] = a * (d ? d[i] * x[i] : x[i]);
+}
+// y = x / sqrt(*s2) or y = x / *s   (normalisation with a device scalar)
+__global__ void __launch_bounds__(kBlock) k_scale_by_inv(long long n, const double *__restrict__ x,
+                                                          const double *__restrict__ s, int is_squared,
+                                                          double *__restrict__ y) {
+  const double nv = is_squared ? sqrt(*s) : *s;
+  const double inv = nv != 0.0 ? 1.0 / nv : 0.0;
+  for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n; i += (long long)gridDim.x * kBlock)
+    y[i] = x[i] * inv;
+}
+// first Chebyshev step from a zero guess: d = D^-1 b / theta ; x = d
+__global__ void __launch_bounds__(kBlock) k_cheb_zero(long long n, const double *__restrict__ b,
+                                                       const double *__restrict__ invd, double inv_theta,
+                                                       double *__restrict__ d, double *__restrict__ x) {
+  for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n; i += (long long)gridDim.x * kBlock) {
+    const double dv = invd[i] * b[i] * inv_theta;
+    d[i] = dv;
+    x[i] = dv;
+  }
+}
+
+// h[i] = V_i . w for i < nvec, h[nvec] = w . w   (one pass over w per group of
+// kMultiDotGroup basis vectors; batched classical Gram-Schmidt of FGMRES, K10)
+__global__ void __launch_bounds__(kBlock) k_multidot(long long n, long long n_dot, const double *__restrict__ w,
+                                                      const double *__restrict__ V, long long ldv, int nvec,
+                                                      int with_norm, Reducer R) {
+  __shared__ double smem[32];
+  const int n_out = nvec + (with_norm ? 1 : 0);
+  for (int g0 = 0; g0 < nvec; g0 += kMultiDotGroup) {
+    double acc[kMultiDotGroup];
+#pragma unroll
+    for (int j = 0; j < kMultiDotGroup; ++j) acc[j] = 0.0;
+    const int ng = min(kMultiDotGroup, nvec - g0);
+    for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n_dot; i += (long long)gridDim.x * kBlock) {
+      const double wi = w[i];
+#pragma unroll
+      for (int j = 0; j < kMultiDotGroup; ++j)
+        if (j < ng) acc[j] += wi * V[(size_t)(g0 + j) * ldv + i];
+    }
+    for (int j = 0; j < ng; ++j) reduce_finalize(acc[j], R, g0 + j, n_out, smem);
+  }
+  if (with_norm) {
+    double s = 0.0;
+    for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n_dot; i += (long long)gridDim.x * kBlock)
+      s += w[i] * w[i];
+    reduce_finalize(s, R, nvec, n_out, smem);
+  }
+}
+// w += sign * sum_i coef[i] V_i     (coef on the device)
+__global__ void __launch_bounds__(kBlock) k_multiaxpy(long long n, double *__restrict__ w, const double *__restrict__ V,
+                                                       long long ldv, int nvec, const double *__restrict__ coef,
+                                                       double sign) {
+  __shared__ double c[128];
+  for (int j = threadIdx.x; j < nvec; j += kBlock) c[j] = sign * coef[j];
+  __syncthreads();
+  for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n; i += (long long)gridDim.x * kBlock) {
+    double s = w[i];
+    for (int j = 0; j < nvec; ++j) s += c[j] * V[(size_t)j * ldv + i];
+    w[i] = s;
+  }
+}
+// h += h2 (tiny)
+__global__ void k_small_add(int n, double *a, const double *b) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] += b[i];
+}
+
+// ---- dense Gauss-Jordan inversion of the coarsest operator (setup, once) ----------
+// aug is [A | I] row-major with ld = 2n
+__global__ void k_gj_pivot(int n, int k, const double *aug, int *piv_row, double *piv_val, int *singular) {
+  __shared__ double sval[kBlock];
+  __shared__ int sidx[kBlock];
+  double best = -1.0;
+  int bi = k;
+  for (int r = k + threadIdx.x; r < n; r += kBlock) {
+    const double a = fabs(aug[(size_t)r * 2 * n + k]);
+    if (a > best) {
+      best = a;
+      bi = r;
+    }
+  }
+  sval[threadIdx.x] = best;
+  sidx[threadIdx.x] = bi;
+  __syncthreads();
+  for (int o = kBlock / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      if (sval[threadIdx.x + o] > sval[threadIdx.x] ||
+          (sval[threadIdx.x + o] == sval[threadIdx.x] && sidx[threadIdx.x + o] < sidx[threadIdx.x])) {
+        sval[threadIdx.x] = sval[threadIdx.x + o];
+        sidx[threadIdx.x] = sidx[threadIdx.x + o];
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    *piv_row = sidx[0];
+    *piv_val = aug[(size_t)sidx[0] * 2 * n + k];
+    if (!(sval[0] > 0.0)) *singular = 1;
+  }
+}
+__global__ void k_gj_swap_scale(int n, int k, double *aug, const int *piv_row, const double *piv_val) {
+  const int p = *piv_row;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  double *rk = aug + (size_t)k * 2 * n, *rp = aug + (size_t)p * 2 * n;
+  const double piv = *piv_val;
+  if (c < 2 * n) {
+    const double a = rp[c], b = rk[c];
+    if (p != k) rp[c] = b;
+    rk[c] = a / piv;
+  }
+}
+__global__ void k_gj_save_col(int n, int k, const double *aug, double *col) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n) col[r] = (r == k) ? 0.0 : aug[(size_t)r * 2 * n + k];
+}
+__global__ void k_gj_eliminate(int n, int k, double *aug, const double *col) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  if (c >= 2 * n) return;
+  const double f = col[r];
+  if (f == 0.0) return;
+  aug[(size_t)r * 2 * n + c] -= f * aug[(size_t)k * 2 * n + c];
+}
+__global__ void k_gj_extract(int n, const double *aug, double *inv) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  if (c < n) inv[(size_t)r * n + c] = aug[(size_t)r * 2 * n + n + c];
+}
+__global__ void k_dense_from_csr(int n, const int *rp, const int *ci, const double *v, double *aug) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  for (int k = rp[r]; k < rp[r + 1]; ++k) aug[(size_t)r * 2 * n + ci[k]] += v[k];
+  aug[(size_t)r * 2 * n + n + r] = 1.0;
+}
+__global__ void k_inv_diag_from_csr(int n, const int *rp, const int *ci, const double *v, double *invd) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  double d = 0.0;
+  for (int k = rp[r]; k < rp[r + 1]; ++k)
+    if (ci[k] == r) d += v[k];
+  invd[r] = 1.0 / d;
+}
+__global__ void k_fill(long long n, double *x, double v) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    x[i] = v;
+}
+__global__ void k_reciprocal(long long n, double *x) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    x[i] = 1.0 / x[i];
+}
+
+}  // namespace fdal

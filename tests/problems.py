@@ -1,0 +1,45 @@
+"""Small seeded problem set shared by the CPU and GPU tests (sizes the oracle
+finishes in seconds)."""
+import functools
+
+import numpy as np
+
+from fictitious_domain_al_preconditioners_b200 import _binding as b
+from fictitious_domain_al_preconditioners_b200 import synthetic as syn
+
+CASES = {
+    # name: (factory, kwargs)
+    "laplace_diag": (syn.immersed_laplace, dict(r_bg=6, diagonal_inverse=True)),
+    "laplace_exact": (syn.immersed_laplace, dict(r_bg=6, diagonal_inverse=False)),
+    "laplace_opform": (syn.immersed_laplace, dict(r_bg=6, operator_form=True, diagonal_inverse=False)),
+    "laplace_opform_diag": (syn.immersed_laplace, dict(r_bg=6, operator_form=True, diagonal_inverse=True)),
+    "stokes2d_exact": (syn.stokes_immersed_boundary, dict(dim=2, nel=32)),
+    "stokes2d_diag": (syn.stokes_immersed_boundary, dict(dim=2, nel=32, diagonal_mass=True)),
+    "stokes2d_minres": (syn.stokes_immersed_boundary, dict(dim=2, nel=16, diagonal_mass=True, diag_minres=True)),
+    "stokes3d_diag": (syn.stokes_immersed_boundary, dict(dim=3, nel=8)),
+    "elliptic_modified": (syn.elliptic_interface, dict(cycle=2)),
+    "elliptic_modified_diag": (syn.elliptic_interface, dict(cycle=2, diagonal_inverse=True)),
+    "elliptic_modified_fixed": (syn.elliptic_interface, dict(cycle=2, fixed_iterations=True)),
+    "elliptic_ideal": (syn.elliptic_interface, dict(cycle=2, modified=False, gamma_solid=10.0)),
+    "elliptic_m2": (syn.elliptic_interface, dict(cycle=1, h_scaled=False, diagonal_inverse=True)),
+}
+
+
+@functools.lru_cache(maxsize=None)
+def get(name):
+    fac, kw = CASES[name]
+    prob = fac(**kw)
+    H = syn.build_hierarchies(prob, max_coarse=300)  # >= 3 levels at these sizes
+    return prob, H
+
+
+def rhs_of(ctx, prob):
+    return ctx.augment_rhs(prob.rhs) if prob.augment_rhs else prob.rhs.copy()
+
+
+def rand(n, seed=0):
+    return np.random.default_rng(seed).uniform(-1.0, 1.0, n)
+
+
+def relerr(a, ref):
+    return float(np.linalg.norm(a - ref) / max(np.linalg.norm(ref), 1e-300))

@@ -1,0 +1,71 @@
+"""The C-ABI shared library loads and exports every symbol include/fdal.h declares
+(no compute calls: there is no GPU on the CPU test box)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from fictitious_domain_al_preconditioners_b200 import _binding as b
+from fictitious_domain_al_preconditioners_b200 import build, lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "fdal.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(fdal_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_the_documented_surface():
+    syms = declared_symbols()
+    for must in ("fdal_create", "fdal_set_csr", "fdal_amg_set_level", "fdal_finalize", "fdal_apply_aug",
+                 "fdal_apply_prec", "fdal_apply_system", "fdal_solve", "fdal_solve_dev", "fdal_destroy"):
+        assert must in syms
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    path = build.build()
+    assert os.path.exists(path)
+    dll = ctypes.CDLL(path)
+    for s in declared_symbols():
+        assert hasattr(dll, s), f"{s} declared in fdal.h but not exported by libfdal.so"
+
+
+def test_binding_table_matches_header():
+    api = lib.load()
+    names = {s[len("fdal_"):] for s in declared_symbols()}
+    bound = set(b.SIGNATURES) | set(b.DEVICE_SIGNATURES)
+    assert names == bound, (names - bound, bound - names)
+    assert api.version().startswith(b"fdal")
+
+
+def test_struct_sizes_match_the_c_side():
+    # fdal_control: 2*int32 + 2*double ; fdal_config: 13 int32/double fields + 3 controls
+    assert ctypes.sizeof(b.Control) == 24
+    assert ctypes.sizeof(b.Config) == 8 + 24 + 8 * 4 + 3 * 24
+    assert ctypes.sizeof(b.SolveInfo) == 8 * 4 + 3 * 8 + 8 + 8 * b.MAX_HISTORY
+    assert ctypes.sizeof(b.CsrView) == 48
+
+
+def test_no_cpu_fallback_without_a_gpu():
+    """On a box without CUDA devices fdal_create must fail loudly (FDAL_ERR_CUDA)."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from fictitious_domain_al_preconditioners_b200 import ALConfig, ALContext, FdalError
+
+    with pytest.raises(FdalError) as e:
+        ALContext(ALConfig())
+    assert e.value.status == b.ERR_CUDA
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "fictitious_domain_al_preconditioners_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".c", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "fdal_oracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, f
