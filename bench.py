@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py — outer FGMRES solve time / DoFs/s of the AL solve path on B200.
+
+One "step" = one complete outer solve (FGMRES right-preconditioned by the
+block-triangular AL preconditioner, inner PCG + AMG V-cycle) of the synthetic
+refinement of the named parameter file.  Prints ONE JSON line (see the contract in
+DESIGN.md "Measurement").
+
+  python bench.py                       # N=1, default workload, few steps
+  python bench.py --impl reference      # the CPU restatement (oracle) on host cores
+  torchrun ... bench.py --gpus N ...    # one rank per GPU (row-partitioned solve)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "outer_fgmres_solve_dofs_per_s"
+UNIT = "DoF/s"
+
+WORKLOADS = {
+    # configs[1]: stokes_immersed_boundary 2D, parameters_stokes.prm as shipped, ~1M DoFs
+    "stokes2d_1M": dict(kind="stokes", dim=2, nel=320, diagonal_mass=False,
+                        label="stokes_immersed_boundary 2D parameters_stokes.prm (exact mass inverses), Q2^2-Q1 nel=320"),
+    # configs[3] family: stokes_immersed_boundary 3D, parameters_stokes_3d.prm (diagonal W^-1, lumped-CG Mp^-1)
+    "stokes3d": dict(kind="stokes", dim=3, nel=32, diagonal_mass=True,
+                     label="stokes_immersed_boundary 3D parameters_stokes_3d.prm, Q2^3-Q1 nel=32"),
+    "stokes2d_diag": dict(kind="stokes", dim=2, nel=320, diagonal_mass=True,
+                          label="stokes_immersed_boundary 2D, diagonal mass, Q2^2-Q1 nel=320"),
+    "laplace": dict(kind="laplace", r_bg=10, label="immersed_laplace 2D circle, Q1 r=10"),
+    "tiny": dict(kind="stokes", dim=2, nel=32, diagonal_mass=True, label="tiny smoke workload"),
+}
+
+
+def build_problem(w):
+    from fictitious_domain_al_preconditioners_b200 import synthetic as syn
+
+    if w["kind"] == "stokes":
+        prob = syn.stokes_immersed_boundary(dim=w["dim"], nel=w["nel"], diagonal_mass=w["diagonal_mass"])
+    else:
+        prob = syn.immersed_laplace(r_bg=w["r_bg"], diagonal_inverse=True)
+    H = syn.build_hierarchies(prob)
+    return prob, H
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self._halt = threading.Event()
+
+    def run(self):
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(
+                    ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                    capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([s.strip() for s in out.split(",")])
+            except Exception:
+                pass
+            self._halt.wait(0.2)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=3)
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples for i in range(4) if len(s) > 2 + i and s[2 + i].lower() == "active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_sample(prob, H, threads, outer_steps=2):
+    """Time the oracle on host cores on a bounded sample: the first `outer_steps` outer
+    iterations of the SAME solve, extrapolated with the full iteration count."""
+    import copy
+
+    from fictitious_domain_al_preconditioners_b200 import synthetic as syn
+    from oracle import oracle
+
+    cfg = copy.deepcopy(prob.config)
+    cfg.outer.max_steps = outer_steps
+    p2 = copy.copy(prob)
+    p2.config = cfg
+    ctx = syn.setup_context(oracle.OracleContext(cfg, threads=threads), p2, H, oracle=True)
+    rhs = ctx.augment_rhs(prob.rhs) if prob.augment_rhs else prob.rhs
+    t0 = time.perf_counter()
+    _, info = ctx.solve(rhs, raise_on_failure=False)
+    dt = time.perf_counter() - t0
+    its = max(1, info.outer_iterations)
+    ctx.close()
+    return dt / its, its  # seconds per outer iteration
+
+
+def run_reference(args, w, wname):
+    """--impl reference: the reference's CPU path.  The reference binary cannot be
+    built here (deal.II / Trilinos / UMFPACK absent), so this times the oracle port
+    with all host threads, on a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle
+
+    api = oracle.load()
+    cores = max(1, min(api.get_max_threads(), os.cpu_count() or 1))
+    prob, H = build_problem(w)
+    # full iteration count of this workload (so the extrapolation is the same as ours):
+    # measured once with a short solve budget if cheap, else taken from the sample itself
+    sample_outer = 2
+    vals = []
+    for i in range(args.warmup + args.steps):
+        per_it, _ = cpu_sample(prob, H, cores, sample_outer)
+        if i >= args.warmup:
+            vals.append(per_it)
+    per_it = float(np.mean(vals))
+    n_outer = args.expected_outer or estimate_outer(w)
+    t_solve = per_it * n_outer
+    value = prob.n_dofs / t_solve
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_solve * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wname, "description": w["label"], "n_dofs": prob.n_dofs},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"first {sample_outer} outer FGMRES iterations of the same solve on {cores} OpenMP threads, "
+                                   f"extrapolated to {n_outer} outer iterations"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+_OUTER_CACHE = {}
+
+
+def estimate_outer(w):
+    """Outer iteration count of the workload (mesh independent): taken from a coarse
+    refinement of the same parameter file solved by the oracle."""
+    key = json.dumps(w, sort_keys=True)
+    if key in _OUTER_CACHE:
+        return _OUTER_CACHE[key]
+    from fictitious_domain_al_preconditioners_b200 import synthetic as syn
+    from oracle import oracle
+
+    w2 = dict(w)
+    if w["kind"] == "stokes":
+        w2["nel"] = 32 if w["dim"] == 2 else 8
+    else:
+        w2["r_bg"] = 6
+    prob, H = build_problem(w2)
+    ctx = syn.setup_context(oracle.OracleContext(prob.config), prob, H, oracle=True)
+    rhs = ctx.augment_rhs(prob.rhs) if prob.augment_rhs else prob.rhs
+    _, info = ctx.solve(rhs, raise_on_failure=False)
+    _OUTER_CACHE[key] = max(1, info.outer_iterations)
+    return _OUTER_CACHE[key]
+
+
+def run_ours(args, w, wname):
+    import torch
+
+    from fictitious_domain_al_preconditioners_b200 import ALContext
+    from fictitious_domain_al_preconditioners_b200 import _binding as b
+    from fictitious_domain_al_preconditioners_b200 import synthetic as syn
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    t0 = time.perf_counter()
+    prob, H = build_problem(w)
+    t_gen = time.perf_counter() - t0
+    prob.config.device = local_rank
+    prob.config.use_graphs = not args.no_graphs
+    t0 = time.perf_counter()
+    ctx = syn.setup_context(ALContext(prob.config), prob, H)
+    t_setup = time.perf_counter() - t0
+    rhs = ctx.augment_rhs(prob.rhs) if prob.augment_rhs else prob.rhs.copy()
+    N = prob.n_dofs
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm: inputs already in HBM --------------------------------
+    d_rhs = torch.from_numpy(rhs).cuda()
+    d_x = torch.zeros(N, dtype=torch.float64, device="cuda")
+    infos = []
+    for _ in range(args.warmup):
+        d_x.zero_()
+        torch.cuda.synchronize()
+        ctx.solve_dev(d_rhs.data_ptr(), d_x.data_ptr())
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    dev_ms = 0.0
+    for _ in range(args.steps):
+        d_x.zero_()
+        torch.cuda.synchronize()
+        info = ctx.solve_dev(d_rhs.data_ptr(), d_x.data_ptr())
+        dev_ms += info.solve_ms
+        infos.append(info)
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    ms_step = dev_ms / args.steps
+    if world > 1:
+        import torch.distributed as dist
+
+        tt = torch.tensor([ms_step], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_step = float(tt.item())
+    x_dev = d_x.cpu().numpy()
+
+    # ---- end-to-end arm: host buffers through the reference-facing C-ABI call ---------
+    h_rhs = torch.from_numpy(rhs).pin_memory()
+    h_x = torch.zeros(N, dtype=torch.float64).pin_memory()
+    e2e_t = []
+    for i in range(min(args.warmup, 1) + args.steps):
+        h_x.zero_()
+        barrier()
+        t0 = time.perf_counter()
+        info = b.SolveInfo()
+        import ctypes as C
+
+        st = ctx.api.solve(ctx._h, C.cast(h_rhs.data_ptr(), C.POINTER(C.c_double)),
+                           C.cast(h_x.data_ptr(), C.POINTER(C.c_double)), C.byref(info))
+        assert st == 0, st
+        barrier()
+        if i >= min(args.warmup, 1):
+            e2e_t.append(time.perf_counter() - t0)
+    e2e_s = float(np.mean(e2e_t))
+    if world > 1:
+        import torch.distributed as dist
+
+        tt = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+
+    # ---- per-kernel roofline, timed live with CUDA events on the library's stream ------
+    peak, peak_src = measured_peak()
+    kern = {}
+    for name, what, param in (("cheb_fine", b.TIME_CHEB_FINE, 0), ("spmv_A", b.TIME_SPMV_A, 0),
+                              ("aug_apply", b.TIME_AUG, 0), ("vcycle", b.TIME_VCYCLE, 0),
+                              ("dot", b.TIME_DOT, 0), ("multidot16", b.TIME_MULTIDOT, 16), ("axpy", b.TIME_AXPY, 0)):
+        try:
+            ms, by, nl = ctx.time_kernel(what, param, warmup=3, reps=20, flush_l2=True)
+            kern[name] = {"ms": ms, "alg_bytes": by, "GBps": by / ms * 1e-6, "frac": by / ms * 1e-6 / peak,
+                          "launches": nl}
+        except Exception as e:  # e.g. multidot without FGMRES basis
+            kern[name] = {"error": str(e)}
+    dom = kern.get("cheb_fine", {})
+    last = infos[-1]
+    total_dofs = N * world  # weak: every rank solves its partition of a world-times larger job
+    if rank == 0:
+        res = {
+            "metric": METRIC, "value": total_dofs / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wname, "description": w["label"], "n_dofs": N, "blocks": list(prob.sizes),
+                       "nnz_A": int(prob.A.nnz), "amg_levels": H[0].describe(),
+                       "l2_policy": "working set (matrices + hierarchy) larger than L2; kernel timings flush L2 "
+                                    "with a 256 MiB memset between launches",
+                       "outer_iterations": int(last.outer_iterations), "inner_iterations": int(last.inner_iterations),
+                       "mass_iterations": int(last.mass_iterations), "final_residual": last.final_residual,
+                       "setup_s": {"generate+amg_host": t_gen, "upload+finalize": t_setup},
+                       "wall_ms_per_step": wall / args.steps * 1e3, "graphs": bool(prob.config.use_graphs)},
+            "e2e": {"value": total_dofs / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 16 * N, "d2h_bytes_per_step": 8 * N,
+                    "ms_per_step": e2e_s * 1e3},
+            "gpu_launches": int(sum(i.kernel_launches for i in infos)),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "k_spmv<TPR,EpiCheb> (fused Chebyshev step, finest AMG level)",
+                         "achieved": dom.get("GBps"), "peak": peak, "unit": "GB/s",
+                         "frac": dom.get("frac"), "traffic": None, "peak_source": peak_src},
+            "kernels": kern,
+        }
+        if not args.no_cpu and world == 1:
+            per_it, _ = cpu_sample(prob, H, threads=1, outer_steps=2)
+            n_outer = int(last.outer_iterations)
+            res["cpu_baseline"] = {"value": N / (per_it * n_outer), "unit": UNIT, "cores": 1, "kind": "port",
+                                   "sample": f"first 2 outer FGMRES iterations of the same solve (oracle, 1 thread = how the "
+                                             f"reference ships), extrapolated to {n_outer} outer iterations",
+                                   "ms_per_step": per_it * n_outer * 1e3}
+        print(json.dumps(res))
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("FDAL_BENCH_WORKLOAD", "stokes2d_1M"))
+    ap.add_argument("--nel", type=int, default=0, help="override the refinement of the workload")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true")
+    ap.add_argument("--expected-outer", type=int, default=0)
+    args = ap.parse_args()
+    w = dict(WORKLOADS[args.workload])
+    if args.nel:
+        w["nel"] = args.nel
+        w["label"] = w["label"].rsplit("nel=", 1)[0] + f"nel={args.nel}"
+    if args.impl == "reference":
+        run_reference(args, w, args.workload)
+    else:
+        run_ours(args, w, args.workload)
+
+
+if __name__ == "__main__":
+    main()

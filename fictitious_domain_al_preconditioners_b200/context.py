@@ -105,6 +105,7 @@ class ALContext:
             raise FdalError(st, "fdal_create failed")
         self._finalized = False
         self.sizes = None
+        self.matrices = set()
 
     # -- lifetime ----------------------------------------------------------
     def close(self):
@@ -130,6 +131,7 @@ class ALContext:
     # -- setup -------------------------------------------------------------
     def set_csr(self, matrix_id: int, A):
         rp, ci, v = b.csr_arrays(A)
+        self.matrices.add(matrix_id)
         self._check(
             self.api.set_csr(
                 self._h,

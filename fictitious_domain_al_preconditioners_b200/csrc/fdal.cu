@@ -58,6 +58,10 @@ struct DevCsr {
   int *rp = nullptr, *ci = nullptr;
   double *v = nullptr;
   bool set = false;
+  // chunk plan of the TMA-staged kernel (k_spmv_stream)
+  int4 *desc = nullptr;
+  int nblk = 0;
+  bool stream_ok = false;
 };
 
 struct AmgLevel {
@@ -103,7 +107,13 @@ static int control_check(ControlState &s, int step, double val) {
 struct CgWs {
   int64_t n = 0;
   double *r = nullptr, *z = nullptr, *p = nullptr, *v = nullptr;
+  double *x = nullptr;     // the iterate lives here so the iteration body is pointer-stable
+  double *bin = nullptr;   // staged right-hand side of the fixed-count mass solve
   double *scal = nullptr;  // S_COUNT device scalars
+  // CUDA graphs: one iteration body (host-checked CG) / one whole fixed-count solve
+  cudaGraphExec_t body_exec = nullptr, fixed_exec = nullptr;
+  int64_t body_nodes = 0, fixed_nodes = 0;
+  bool graph_ok = true;
 };
 
 }  // namespace fdal
@@ -137,10 +147,13 @@ struct fdal_ctx {
   double *mr_u[3] = {nullptr, nullptr, nullptr}, *mr_m[3] = {nullptr, nullptr, nullptr}, *mr_v = nullptr;
   char *flush_buf = nullptr;
   size_t flush_bytes = 0;
+  double *mass_cta_ws = nullptr;       // 5*m scratch of k_mass_pcg_cta (m <= kMassCtaMaxRows)
   int mass_its_m = 0, mass_its_p = 0;  // calibrated fixed iteration counts (exact mass solves)
   // counters
   int its_a11 = 0, its_a22 = 0, its_mass = 0, n_inner_solves = 0;
-  int64_t launches = 0;
+  int64_t launches = 0, graph_launches = 0;
+  int stream_ctas_per_sm = 4, spmv_unroll = 1;
+  bool prefer_stream = true;
   int fail = 0;
   std::vector<void *> allocs;
   std::string err;
@@ -185,7 +198,7 @@ static int dvec(fdal_ctx *c, double **p, int64_t n) {
 }
 
 static int choose_tpr(double avg) {
-  static const char *env = getenv("FDAL_TPR");
+  const char *env = getenv("FDAL_TPR");
   if (env) {
     int t = atoi(env);
     if (t == 2 || t == 4 || t == 8 || t == 16 || t == 32) return t;
@@ -203,9 +216,12 @@ static int upload_csr(fdal_ctx *c, const HostCsr &h, DevCsr &d) {
     return FDAL_ERR_UNSUPPORTED;
   }
   int st;
+  // +8 zero-filled pad elements: the bulk copies of k_spmv_stream are 16-byte granular
   if ((st = dmalloc(c, &d.rp, (size_t)h.nr + 1))) return st;
-  if ((st = dmalloc(c, &d.ci, (size_t)h.nnz))) return st;
-  if ((st = dmalloc(c, &d.v, (size_t)h.nnz))) return st;
+  if ((st = dmalloc(c, &d.ci, (size_t)h.nnz + 8))) return st;
+  if ((st = dmalloc(c, &d.v, (size_t)h.nnz + 8))) return st;
+  CU(cudaMemsetAsync(d.ci + h.nnz, 0, 8 * sizeof(int), c->stream));
+  CU(cudaMemsetAsync(d.v + h.nnz, 0, 8 * sizeof(double), c->stream));
   CU(cudaMemcpyAsync(d.rp, h.rp.data(), ((size_t)h.nr + 1) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
   if (h.nnz) {
     CU(cudaMemcpyAsync(d.ci, h.ci.data(), (size_t)h.nnz * sizeof(int), cudaMemcpyHostToDevice, c->stream));
@@ -220,6 +236,28 @@ static int upload_csr(fdal_ctx *c, const HostCsr &h, DevCsr &d) {
   d.d.v = d.v;
   d.d.tpr = choose_tpr(h.nr ? (double)h.nnz / (double)h.nr : 1.0);
   d.set = true;
+  // chunk plan: runs of whole rows whose 4-aligned non-zero range fits kChunk
+  {
+    const bool no_stream = getenv("FDAL_NO_STREAM") != nullptr;
+    std::vector<int4> rb;
+    bool ok = !no_stream && h.nr > 0;
+    int64_t r0 = 0;
+    while (ok && r0 < h.nr) {
+      const int e0 = h.rp[r0] & ~3;
+      int64_t r1 = r0;
+      while (r1 < h.nr && r1 - r0 < 4096 && ((h.rp[r1 + 1] + 3) & ~3) - e0 <= kChunk) ++r1;
+      if (r1 == r0) ok = false;  // a single row longer than a chunk: keep the row-group kernel
+      rb.push_back(make_int4((int)r0, (int)r1, e0, ((h.rp[r1] + 3) & ~3) - e0));
+      r0 = r1;
+    }
+    if (ok) {
+      d.nblk = (int)rb.size();
+      if ((st = dmalloc(c, &d.desc, rb.size()))) return st;
+      CU(cudaMemcpyAsync(d.desc, rb.data(), rb.size() * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+      d.stream_ok = true;
+    }
+  }
   return FDAL_OK;
 }
 
@@ -236,18 +274,59 @@ static inline int grid_elems(const fdal_ctx *c, long long n) {
 static inline Reducer reducer(fdal_ctx *c, double *out) { return Reducer{c->d_partials, c->d_counter, out}; }
 static inline XVec xv(const double *x) { return XVec{x, nullptr, std::numeric_limits<int>::max()}; }
 
+template <class Epi, bool TWO>
+static void spmv_stream(fdal_ctx *c, const DevCsr &A, const double *x, const DevCsr *B2, const double *t2, Epi epi,
+                        double *red_out) {
+  const int g = std::max(1, std::min(A.nblk, c->sms * c->stream_ctas_per_sm));
+  Reducer R = reducer(c, red_out);
+  XVec X = xv(x);
+  StreamPlan plan{A.desc, A.nblk};
+  CsrDev b2 = B2 ? B2->d : CsrDev();
+  const size_t sm = kStreamSmemBytes;
+  static bool attr_done = false;  // per (Epi, TWO) instantiation
+  if (!attr_done) {
+    cudaFuncSetAttribute(k_spmv_stream<2, Epi, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    cudaFuncSetAttribute(k_spmv_stream<4, Epi, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    cudaFuncSetAttribute(k_spmv_stream<8, Epi, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    cudaFuncSetAttribute(k_spmv_stream<16, Epi, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    cudaFuncSetAttribute(k_spmv_stream<32, Epi, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    attr_done = true;
+  }
+  switch (A.d.tpr) {
+    case 2: k_spmv_stream<2, Epi, TWO><<<g, kBlock, sm, c->stream>>>(A.d, plan, X, b2, t2, epi, R); break;
+    case 4: k_spmv_stream<4, Epi, TWO><<<g, kBlock, sm, c->stream>>>(A.d, plan, X, b2, t2, epi, R); break;
+    case 8: k_spmv_stream<8, Epi, TWO><<<g, kBlock, sm, c->stream>>>(A.d, plan, X, b2, t2, epi, R); break;
+    case 16: k_spmv_stream<16, Epi, TWO><<<g, kBlock, sm, c->stream>>>(A.d, plan, X, b2, t2, epi, R); break;
+    default: k_spmv_stream<32, Epi, TWO><<<g, kBlock, sm, c->stream>>>(A.d, plan, X, b2, t2, epi, R); break;
+  }
+  c->launches++;
+}
 template <class Epi>
 static void spmv(fdal_ctx *c, const DevCsr &A, const double *x, Epi epi, double *red_out = nullptr) {
   if (A.d.nrows == 0) return;
+  if (A.stream_ok && c->prefer_stream) {
+    spmv_stream<Epi, false>(c, A, x, nullptr, nullptr, epi, red_out);
+    return;
+  }
   const int g = grid_rows(c, A.d.nrows, A.d.tpr);
   Reducer R = reducer(c, red_out);
   XVec X = xv(x);
-  switch (A.d.tpr) {
-    case 2: k_spmv<2, Epi><<<g, kBlock, 0, c->stream>>>(A.d, X, epi, R); break;
-    case 4: k_spmv<4, Epi><<<g, kBlock, 0, c->stream>>>(A.d, X, epi, R); break;
-    case 8: k_spmv<8, Epi><<<g, kBlock, 0, c->stream>>>(A.d, X, epi, R); break;
-    case 16: k_spmv<16, Epi><<<g, kBlock, 0, c->stream>>>(A.d, X, epi, R); break;
-    default: k_spmv<32, Epi><<<g, kBlock, 0, c->stream>>>(A.d, X, epi, R); break;
+  if (c->spmv_unroll > 1) {
+    switch (A.d.tpr) {
+      case 2: k_spmv<2, Epi, 4><<<g, kBlock, 0, c->stream>>>(A.d, X, epi, R); break;
+      case 4: k_spmv<4, Epi, 4><<<g, kBlock, 0, c->stream>>>(A.d, X, epi, R); break;
+      case 8: k_spmv<8, Epi, 4><<<g, kBlock, 0, c->stream>>>(A.d, X, epi, R); break;
+      case 16: k_spmv<16, Epi, 4><<<g, kBlock, 0, c->stream>>>(A.d, X, epi, R); break;
+      default: k_spmv<32, Epi, 4><<<g, kBlock, 0, c->stream>>>(A.d, X, epi, R); break;
+    }
+  } else {
+    switch (A.d.tpr) {
+      case 2: k_spmv<2, Epi><<<g, kBlock, 0, c->stream>>>(A.d, X, epi, R); break;
+      case 4: k_spmv<4, Epi><<<g, kBlock, 0, c->stream>>>(A.d, X, epi, R); break;
+      case 8: k_spmv<8, Epi><<<g, kBlock, 0, c->stream>>>(A.d, X, epi, R); break;
+      case 16: k_spmv<16, Epi><<<g, kBlock, 0, c->stream>>>(A.d, X, epi, R); break;
+      default: k_spmv<32, Epi><<<g, kBlock, 0, c->stream>>>(A.d, X, epi, R); break;
+    }
   }
   c->launches++;
 }
@@ -255,15 +334,29 @@ template <class Epi>
 static void spmv2(fdal_ctx *c, const DevCsr &A, const double *x, const DevCsr &Ct, const double *t, Epi epi,
                   double *red_out = nullptr) {
   if (A.d.nrows == 0) return;
+  if (A.stream_ok && c->prefer_stream) {
+    spmv_stream<Epi, true>(c, A, x, &Ct, t, epi, red_out);
+    return;
+  }
   const int g = grid_rows(c, A.d.nrows, A.d.tpr);
   Reducer R = reducer(c, red_out);
   XVec X = xv(x);
-  switch (A.d.tpr) {
-    case 2: k_spmv2<2, Epi><<<g, kBlock, 0, c->stream>>>(A.d, X, Ct.d, t, epi, R); break;
-    case 4: k_spmv2<4, Epi><<<g, kBlock, 0, c->stream>>>(A.d, X, Ct.d, t, epi, R); break;
-    case 8: k_spmv2<8, Epi><<<g, kBlock, 0, c->stream>>>(A.d, X, Ct.d, t, epi, R); break;
-    case 16: k_spmv2<16, Epi><<<g, kBlock, 0, c->stream>>>(A.d, X, Ct.d, t, epi, R); break;
-    default: k_spmv2<32, Epi><<<g, kBlock, 0, c->stream>>>(A.d, X, Ct.d, t, epi, R); break;
+  if (c->spmv_unroll > 1) {
+    switch (A.d.tpr) {
+      case 2: k_spmv2<2, Epi, 4><<<g, kBlock, 0, c->stream>>>(A.d, X, Ct.d, t, epi, R); break;
+      case 4: k_spmv2<4, Epi, 4><<<g, kBlock, 0, c->stream>>>(A.d, X, Ct.d, t, epi, R); break;
+      case 8: k_spmv2<8, Epi, 4><<<g, kBlock, 0, c->stream>>>(A.d, X, Ct.d, t, epi, R); break;
+      case 16: k_spmv2<16, Epi, 4><<<g, kBlock, 0, c->stream>>>(A.d, X, Ct.d, t, epi, R); break;
+      default: k_spmv2<32, Epi, 4><<<g, kBlock, 0, c->stream>>>(A.d, X, Ct.d, t, epi, R); break;
+    }
+  } else {
+    switch (A.d.tpr) {
+      case 2: k_spmv2<2, Epi><<<g, kBlock, 0, c->stream>>>(A.d, X, Ct.d, t, epi, R); break;
+      case 4: k_spmv2<4, Epi><<<g, kBlock, 0, c->stream>>>(A.d, X, Ct.d, t, epi, R); break;
+      case 8: k_spmv2<8, Epi><<<g, kBlock, 0, c->stream>>>(A.d, X, Ct.d, t, epi, R); break;
+      case 16: k_spmv2<16, Epi><<<g, kBlock, 0, c->stream>>>(A.d, X, Ct.d, t, epi, R); break;
+      default: k_spmv2<32, Epi><<<g, kBlock, 0, c->stream>>>(A.d, X, Ct.d, t, epi, R); break;
+    }
   }
   c->launches++;
 }
@@ -402,12 +495,58 @@ static void cg_body(fdal_ctx *c, CgWs &w, const OpFn &op, const OpFn &prec, doub
                                                                reducer(c, w.scal + S_RR));
   c->launches++;
 }
-// deal.II SolverCG from a zero initial guess (inverse_operator), host-checked control
+static bool stream_is_capturing(fdal_ctx *c) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(c->stream, &cs);
+  return cs != cudaStreamCaptureStatusNone;
+}
+// Capture `enqueue` (kernel launches on c->stream only, no host interaction) into an
+// executable graph.  On failure the caller keeps launching directly.
+static bool capture_graph(fdal_ctx *c, const std::function<void()> &enqueue, cudaGraphExec_t *exec, int64_t *nodes) {
+  const int64_t l0 = c->launches;
+  if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  enqueue();
+  cudaGraph_t g = nullptr;
+  cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+  *nodes = c->launches - l0;
+  c->launches = l0;  // nothing ran yet
+  if (e != cudaSuccess || !g) {
+    cudaGetLastError();
+    return false;
+  }
+  e = cudaGraphInstantiate(exec, g, 0);
+  cudaGraphDestroy(g);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    *exec = nullptr;
+    return false;
+  }
+  return true;
+}
+static void run_cg_body(fdal_ctx *c, CgWs &w, const OpFn &op, const OpFn &prec, bool capturable) {
+  if (c->cfg.use_graphs && capturable && w.graph_ok && !stream_is_capturing(c)) {
+    if (!w.body_exec)
+      w.graph_ok = capture_graph(c, [&]() { cg_body(c, w, op, prec, w.x); }, &w.body_exec, &w.body_nodes);
+    if (w.body_exec) {
+      cudaGraphLaunch(w.body_exec, c->stream);
+      c->launches += w.body_nodes;
+      c->graph_launches++;
+      return;
+    }
+  }
+  cg_body(c, w, op, prec, w.x);
+}
+// deal.II SolverCG from a zero initial guess (inverse_operator), host-checked control.
+// `capturable`: op and prec never synchronise with the host, so one iteration body is
+// replayed as a CUDA graph (pointer-stable: the iterate lives in w.x).
 static int cg_solve(fdal_ctx *c, CgWs &w, const OpFn &op, const OpFn &prec, const fdal_control &ctl, const double *b,
-                    double *x, int *its_out, int fail_code) {
+                    double *x, int *its_out, int fail_code, bool capturable) {
   ControlState cs;
   cs.c = ctl;
-  cg_start(c, w, b, x);
+  cg_start(c, w, b, w.x);
   dot(c, w.n, w.r, w.r, w.scal + S_RR);
   double rr;
   int st = read_scalars(c, w.scal + S_RR, 1, &rr);
@@ -416,11 +555,12 @@ static int cg_solve(fdal_ctx *c, CgWs &w, const OpFn &op, const OpFn &prec, cons
   int it = 0;
   while (state == ST_ITERATE) {
     ++it;
-    cg_body(c, w, op, prec, x);
+    run_cg_body(c, w, op, prec, capturable);
     st = read_scalars(c, w.scal + S_RR, 1, &rr);
     if (st) return st;
     state = control_check(cs, it, std::sqrt(std::fabs(rr)));
   }
+  dcopy(c, w.n, w.x, x);
   *its_out = it;
   return state == ST_SUCCESS ? FDAL_OK : fail_code;
 }
@@ -432,10 +572,25 @@ static void mass_prec(fdal_ctx *c, const double *invdiag, int64_t n, const doubl
 }
 static void mass_solve_fixed(fdal_ctx *c, CgWs &w, const DevCsr &M, const double *invdiag, int its, const double *b,
                              double *x) {
-  cg_start(c, w, b, x);
   OpFn op = [&](const double *in, double *out, double *d) { spmv(c, M, in, EpiDotX{out, in}, d); };
   OpFn pr = [&](const double *r, double *z, double *d) { mass_prec(c, invdiag, w.n, r, z, d); };
-  for (int i = 0; i < its; ++i) cg_body(c, w, op, pr, x);
+  auto whole = [&]() {
+    cg_start(c, w, w.bin, w.x);
+    for (int i = 0; i < its; ++i) cg_body(c, w, op, pr, w.x);
+  };
+  dcopy(c, w.n, b, w.bin);
+  bool done = false;
+  if (c->cfg.use_graphs && w.graph_ok && !stream_is_capturing(c)) {
+    if (!w.fixed_exec) w.graph_ok = capture_graph(c, whole, &w.fixed_exec, &w.fixed_nodes);
+    if (w.fixed_exec) {
+      cudaGraphLaunch(w.fixed_exec, c->stream);
+      c->launches += w.fixed_nodes;
+      c->graph_launches++;
+      done = true;
+    }
+  }
+  if (!done) whole();
+  dcopy(c, w.n, w.x, x);
 }
 static int mass_calibrate(fdal_ctx *c, CgWs &w, const DevCsr &M, const double *invdiag, int *its_out) {
   // count the iterations Jacobi-PCG needs to push the recursive residual below
@@ -447,11 +602,8 @@ static int mass_calibrate(fdal_ctx *c, CgWs &w, const DevCsr &M, const double *i
     s = s * 6364136223846793005ull + 1442695040888963407ull;
     hb[(size_t)i] = ((double)(s >> 11) / 9007199254740992.0) * 2.0 - 1.0;
   }
-  double *b = nullptr;
-  int st = dvec(c, &b, n);
-  if (st) return st;
-  double *x = nullptr;
-  if ((st = dvec(c, &x, n))) return st;
+  double *b = w.bin, *x = w.x;
+  int st;
   CU(cudaMemcpyAsync(b, hb.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   cg_start(c, w, b, x);
   dot(c, n, w.r, w.r, w.scal + S_RR);
@@ -479,19 +631,30 @@ static bool is_elliptic(const fdal_ctx *c) {
   return c->cfg.kind == FDAL_KIND_ELLIPTIC_IDEAL || c->cfg.kind == FDAL_KIND_ELLIPTIC_MODIFIED;
 }
 
-// y = a * invW x   (K4 / K5).  x and y must be distinct buffers (and not t_mw).
-static void apply_winv_scaled(fdal_ctx *c, double a, const double *x, double *y) {
+// y = a * invW x (+ add)   (K4 / K5).  x and y must be distinct buffers (and not t_mw).
+static void apply_winv_scaled(fdal_ctx *c, double a, const double *x, double *y, const double *add = nullptr) {
   const int64_t m = c->m;
   if (c->cfg.winv_mode == FDAL_WINV_DIAG) {
     diag_scale(c, m, a, c->d_winv, x, y);
-  } else if (c->cfg.winv_mode == FDAL_WINV_EXACT_M) {
+    if (add) axpby(c, m, 1.0, add, 1.0, y);
+    return;
+  }
+  const int repeat = c->cfg.winv_mode == FDAL_WINV_EXACT_M ? 1 : 2;
+  if (c->mass_cta_ws) {
+    // whole fixed-count PCG (both applications of M^-1 for W = M^2) in one CTA
+    k_mass_pcg_cta<<<1, kMassCtaThreads, 0, c->stream>>>(c->dmat[FDAL_MAT_M].d, c->d_m_invdiag, c->mass_its_m, repeat,
+                                                         a, x, add, y, c->mass_cta_ws);
+    c->launches++;
+    return;
+  }
+  if (repeat == 1) {
     mass_solve_fixed(c, c->cgmass_m, c->dmat[FDAL_MAT_M], c->d_m_invdiag, c->mass_its_m, x, y);
-    dscale(c, m, a, y);
   } else {
     mass_solve_fixed(c, c->cgmass_m, c->dmat[FDAL_MAT_M], c->d_m_invdiag, c->mass_its_m, x, c->t_mw);
     mass_solve_fixed(c, c->cgmass_m, c->dmat[FDAL_MAT_M], c->d_m_invdiag, c->mass_its_m, c->t_mw, y);
-    dscale(c, m, a, y);
   }
+  dscale(c, m, a, y);
+  if (add) axpby(c, m, 1.0, add, 1.0, y);
 }
 // Mp_inv (stokes_immersed_boundary.cc:931-963)
 static int apply_mp_inv(fdal_ctx *c, const double *x, double *y) {
@@ -502,7 +665,7 @@ static int apply_mp_inv(fdal_ctx *c, const double *x, double *y) {
   OpFn op = [&](const double *in, double *out, double *d) { spmv(c, c->dmat[FDAL_MAT_MP], in, EpiDotX{out, in}, d); };
   OpFn pr = [&](const double *r, double *z, double *d) { mass_prec(c, c->d_mp_lumped, c->n1, r, z, d); };
   int its = 0;
-  int st = cg_solve(c, c->cgmass_p, op, pr, c->cfg.mass, x, y, &its, FDAL_ERR_MASS_NO_CONVERGENCE);
+  int st = cg_solve(c, c->cgmass_p, op, pr, c->cfg.mass, x, y, &its, FDAL_ERR_MASS_NO_CONVERGENCE, true);
   c->its_mass += its;
   if (st && !c->fail) c->fail = st;
   return st;
@@ -515,8 +678,7 @@ static void couple_phase1(fdal_ctx *c, const double *x, double a, const double *
     spmv(c, C, x, EpiCouple{t, c->d_winv, a, add, y1});
   } else {
     spmv(c, C, x, EpiCouple{c->t_m1, nullptr, 1.0, nullptr, y1});
-    apply_winv_scaled(c, a, c->t_m1, t);
-    if (add) axpby(c, c->m, 1.0, add, 1.0, t);
+    apply_winv_scaled(c, a, c->t_m1, t, add);
   }
 }
 
@@ -642,7 +804,10 @@ static int apply_aug_inv(fdal_ctx *c, int which, const double *b, double *x, int
       dcopy(c, w.n, r, z);
       dot(c, w.n, r, z, d);
     };
-  int st = cg_solve(c, w, op, pr, c->cfg.inner, b, x, its, FDAL_ERR_INNER_NO_CONVERGENCE);
+  // the only non-capturable body: the no-grad-div Stokes operator nests a host-checked Mp CG
+  const bool capturable = !(which == FDAL_AMG_A11 && is_stokes(c) && c->cfg.grad_div_in_operator &&
+                            c->cfg.mp_inv_mode == FDAL_MPINV_CG_LUMPED);
+  int st = cg_solve(c, w, op, pr, c->cfg.inner, b, x, its, FDAL_ERR_INNER_NO_CONVERGENCE, capturable);
   if (which == FDAL_AMG_A11)
     c->its_a11 += *its;
   else
@@ -698,7 +863,7 @@ static int apply_prec(fdal_ctx *c, const double *u, double *v) {
           dcopy(c, c->n0 + c->n1, r, z);
           dot(c, c->n0 + c->n1, r, z, d);
         };
-      int st = cg_solve(c, c->cgblk, op, pr, c->cfg.inner, uu, v, &its, FDAL_ERR_INNER_NO_CONVERGENCE);
+      int st = cg_solve(c, c->cgblk, op, pr, c->cfg.inner, uu, v, &its, FDAL_ERR_INNER_NO_CONVERGENCE, true);
       c->its_a11 += its;
       c->n_inner_solves++;
       if (st && !c->fail) c->fail = st;
@@ -991,6 +1156,8 @@ static int alloc_cg(fdal_ctx *c, CgWs &w, int64_t n) {
   if ((st = dvec(c, &w.z, n))) return st;
   if ((st = dvec(c, &w.p, n))) return st;
   if ((st = dvec(c, &w.v, n))) return st;
+  if ((st = dvec(c, &w.x, n))) return st;
+  if ((st = dvec(c, &w.bin, n))) return st;
   if ((st = dvec(c, &w.scal, S_COUNT))) return st;
   return FDAL_OK;
 }
@@ -1039,6 +1206,10 @@ int fdal_create(fdal_ctx **out, const fdal_config *cfg) {
     return FDAL_ERR_CUDA;
   }
   cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, cfg->device);
+  // tuning knobs (measurement only; defaults are the shipped configuration)
+  if (const char *e = getenv("FDAL_SPMV")) c->prefer_stream = strcmp(e, "classic") != 0;
+  if (const char *e = getenv("FDAL_UNROLL")) c->spmv_unroll = atoi(e);
+  if (const char *e = getenv("FDAL_STREAM_CTAS")) c->stream_ctas_per_sm = std::max(1, atoi(e));
   *out = c;
   return FDAL_OK;
 }
@@ -1047,6 +1218,10 @@ void fdal_destroy(fdal_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->cfg.device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  for (CgWs *w : {&c->cg11, &c->cg22, &c->cgblk, &c->cgmass_m, &c->cgmass_p}) {
+    if (w->body_exec) cudaGraphExecDestroy(w->body_exec);
+    if (w->fixed_exec) cudaGraphExecDestroy(w->fixed_exec);
+  }
   for (void *p : c->allocs) cudaFree(p);
   if (c->h_scal) cudaFreeHost(c->h_scal);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -1245,6 +1420,8 @@ int fdal_finalize(fdal_ctx *c) {
     if ((st = alloc_cg(c, c->cgmass_m, c->m))) return st;
     if ((st = invdiag_of(c, c->dmat[FDAL_MAT_M], &c->d_m_invdiag))) return st;
     if ((st = mass_calibrate(c, c->cgmass_m, c->dmat[FDAL_MAT_M], c->d_m_invdiag, &c->mass_its_m))) return st;
+    static const bool no_cta = getenv("FDAL_NO_MASS_CTA") != nullptr;
+    if (c->m <= kMassCtaMaxRows && !no_cta && (st = dvec(c, &c->mass_cta_ws, 5 * c->m))) return st;
   }
   if (is_stokes(c)) {
     if ((st = alloc_cg(c, c->cgmass_p, c->n1))) return st;

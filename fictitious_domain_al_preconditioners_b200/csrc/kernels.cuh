@@ -175,7 +175,29 @@ struct EpiCheb {
 };
 
 // ---- CSR SpMV, TPR threads per row, grid-stride over row chunks ----------------
-template <int TPR, class Epi>
+// row-group partial sum with U independent (value, column, x) load chains in flight
+template <int TPR, int U>
+__device__ __forceinline__ double row_partial(const CsrDev &A, const XVec &X, int k0, int k1, int lane) {
+  double s = 0.0;
+  int k = k0 + lane;
+  if (U > 1) {
+    for (; k + (U - 1) * TPR < k1; k += U * TPR) {
+      double vv[U];
+      int cc[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        vv[u] = __ldg(A.v + k + u * TPR);
+        cc[u] = __ldg(A.ci + k + u * TPR);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) s += vv[u] * xload(X, cc[u]);
+    }
+  }
+  for (; k < k1; k += TPR) s += __ldg(A.v + k) * xload(X, __ldg(A.ci + k));
+  return s;
+}
+
+template <int TPR, class Epi, int U = 1>
 __global__ void __launch_bounds__(kBlock) k_spmv(CsrDev A, XVec X, Epi epi, Reducer R) {
   __shared__ double smem[32];
   constexpr int rows_per_block = kBlock / TPR;
@@ -188,7 +210,7 @@ __global__ void __launch_bounds__(kBlock) k_spmv(CsrDev A, XVec X, Epi epi, Redu
     double s = 0.0;
     if (row < A.nrows) {
       const int k0 = __ldg(A.rp + row), k1 = __ldg(A.rp + row + 1);
-      for (int k = k0 + lane; k < k1; k += TPR) s += __ldg(A.v + k) * xload(X, __ldg(A.ci + k));
+      s = row_partial<TPR, U>(A, X, k0, k1, lane);
     }
 #pragma unroll
     for (int o = TPR >> 1; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, TPR);
@@ -201,7 +223,7 @@ __global__ void __launch_bounds__(kBlock) k_spmv(CsrDev A, XVec X, Epi epi, Redu
 // Two CSR matrices with the same row partition are walked in one row pass, so A x
 // never goes to memory before the coupling term is added (K3).  t already carries
 // gamma * W^-1 C x (phase 1), and for the block system also + x1.
-template <int TPR, class Epi>
+template <int TPR, class Epi, int U = 1>
 __global__ void __launch_bounds__(kBlock) k_spmv2(CsrDev A, XVec X, CsrDev Ct, const double *__restrict__ t, Epi epi,
                                                    Reducer R) {
   __shared__ double smem[32];
@@ -216,7 +238,7 @@ __global__ void __launch_bounds__(kBlock) k_spmv2(CsrDev A, XVec X, CsrDev Ct, c
     if (row < A.nrows) {
       const int k0 = __ldg(A.rp + row), k1 = __ldg(A.rp + row + 1);
       const int c0 = __ldg(Ct.rp + row), c1 = __ldg(Ct.rp + row + 1);
-      for (int k = k0 + lane; k < k1; k += TPR) s += __ldg(A.v + k) * xload(X, __ldg(A.ci + k));
+      s = row_partial<TPR, U>(A, X, k0, k1, lane);
       for (int k = c0 + lane; k < c1; k += TPR) s += __ldg(Ct.v + k) * __ldg(t + __ldg(Ct.ci + k));
     }
 #pragma unroll
@@ -224,6 +246,130 @@ __global__ void __launch_bounds__(kBlock) k_spmv2(CsrDev A, XVec X, CsrDev Ct, c
     if (lane == 0 && row < A.nrows) contrib += epi((int)row, s);
   }
   if (Epi::kReduce) reduce_finalize(contrib, R, 0, 1, smem);
+}
+
+// ---- TMA-staged CSR SpMV ("stream" variant, the default) ---------------------------
+// The value / column arrays of a run of whole rows (a "chunk", <= kChunk non-zeros,
+// row-aligned, built once at upload) are one contiguous byte range each, so a single
+// elected thread moves them global -> shared with two 1-D bulk copies
+// (cp.async.bulk, SASS UBLKCP) that complete on an mbarrier.  CTAs are persistent and
+// double-buffered: while chunk i is processed, chunk i+1 is already in flight, so
+// the HBM stream never waits for the latency-bound x gathers.  Phase A: every
+// thread multiplies kChunk/kBlock staged non-zeros with gathered x (independent
+// gathers, mostly L2 hits) and parks the products in shared memory.  Phase B: TPR
+// lanes per row reduce the row's products from shared memory (conflict-free) and run
+// the fused epilogue.  With TWO a second CSR matrix with the same rows (Ct, a handful
+// of non-zeros) is added from global memory in phase B: y = A x + Ct t in one pass.
+constexpr int kChunk = 2048;
+constexpr int kChunkCap = kChunk + 8;
+constexpr int kStreamSmemBytes = 2 * kChunkCap * 8 + 2 * kChunkCap * 4 + kChunkCap * 8 + 32;
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+struct StreamPlan {
+  const int4 *desc;  // [nblk] {first row, end row, first element (4-aligned), element count (4-aligned)}
+  int nblk;
+};
+
+template <int TPR, class Epi, bool TWO>
+__global__ void __launch_bounds__(kBlock) k_spmv_stream(CsrDev A, StreamPlan plan, XVec X, CsrDev B2,
+                                                         const double *__restrict__ t2, Epi epi, Reducer R) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *sv = reinterpret_cast<double *>(smem_raw);                     // [2][kChunkCap]
+  double *sprod = sv + 2 * kChunkCap;                                    // [kChunkCap]
+  int *sci = reinterpret_cast<int *>(sprod + kChunkCap);                 // [2][kChunkCap]
+  unsigned long long *bar = reinterpret_cast<unsigned long long *>(sci + 2 * kChunkCap);  // [2]
+  __shared__ double red_smem[32];
+
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  auto issue = [&](int blk, int stage) {
+    const int4 dsc = __ldg(plan.desc + blk);
+    const int e0 = dsc.z;
+    const unsigned n = (unsigned)dsc.w;
+    if (n) {
+      mbar_expect_tx(&bar[stage], n * 12u);
+      bulk_g2s(sv + stage * kChunkCap, A.v + e0, n * 8u, &bar[stage]);
+      bulk_g2s(sci + stage * kChunkCap, A.ci + e0, n * 4u, &bar[stage]);
+    }
+  };
+
+  unsigned parity[2] = {0u, 0u};
+  int stage = 0;
+  double contrib = 0.0;
+  if (tid == 0 && (int)blockIdx.x < plan.nblk) issue(blockIdx.x, 0);
+
+  constexpr int groups = kBlock / TPR;
+  const int lane = tid & (TPR - 1);
+  const int group = tid / TPR;
+
+  for (int blk = blockIdx.x; blk < plan.nblk; blk += gridDim.x) {
+    const int nxt = blk + gridDim.x;
+    if (tid == 0 && nxt < plan.nblk) issue(nxt, stage ^ 1);
+    const int4 dsc = __ldg(plan.desc + blk);
+    const int r0 = dsc.x, r1 = dsc.y, e0 = dsc.z, n = dsc.w;
+    if (n) {
+      mbar_wait(&bar[stage], parity[stage]);
+      parity[stage] ^= 1u;
+    }
+    // phase A: products of the staged non-zeros with gathered x
+    const double *cv = sv + stage * kChunkCap;
+    const int *cc = sci + stage * kChunkCap;
+#pragma unroll 4
+    for (int j = tid; j < n; j += kBlock) sprod[j] = cv[j] * xload(X, cc[j]);
+    __syncthreads();
+    // phase B: per-row reduction + fused epilogue
+    const int nrows = r1 - r0;
+    for (int base = 0; base < nrows; base += groups) {
+      const int row = r0 + base + group;
+      double s = 0.0;
+      if (row < r1) {
+        const int k0 = __ldg(A.rp + row) - e0, k1 = __ldg(A.rp + row + 1) - e0;
+        for (int k = k0 + lane; k < k1; k += TPR) s += sprod[k];
+        if (TWO) {
+          const int c0 = __ldg(B2.rp + row), c1 = __ldg(B2.rp + row + 1);
+          for (int k = c0 + lane; k < c1; k += TPR) s += __ldg(B2.v + k) * __ldg(t2 + __ldg(B2.ci + k));
+        }
+      }
+#pragma unroll
+      for (int o = TPR >> 1; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, TPR);
+      if (lane == 0 && row < r1) contrib += epi(row, s);
+    }
+    __syncthreads();  // sprod and this stage's buffers are free again
+    stage ^= 1;
+  }
+  if (Epi::kReduce) reduce_finalize(contrib, R, 0, 1, red_smem);
 }
 
 // ---- dense GEMV for the coarsest AMG level: y = Ainv b (one warp per row) --------
@@ -263,11 +409,13 @@ __global__ void __launch_bounds__(kBlock) k_diag_prec_dot(long long n, const dou
   }
   reduce_finalize(s, R, 0, 1, smem);
 }
-// p = z + beta p, beta = rho / rho_old (rho_old = +inf on the first iteration => p = z)
+// p = z + beta p, beta = rho / rho_old (rho_old = +inf on the first iteration => p = z;
+// rho_old == 0 only when the residual is exactly zero, e.g. a zero right-hand side in
+// a fixed-count mass solve: the iterate is frozen instead of producing 0/0)
 __global__ void __launch_bounds__(kBlock) k_cg_update_p(long long n, const double *__restrict__ z, double *__restrict__ p,
                                                          const double *__restrict__ scal) {
   const double rho = scal[S_RHO], rho_old = scal[S_RHO_OLD];
-  const double beta = isinf(rho_old) ? 0.0 : rho / rho_old;
+  const double beta = (isinf(rho_old) || rho_old == 0.0) ? 0.0 : rho / rho_old;
   for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n; i += (long long)gridDim.x * kBlock)
     p[i] = z[i] + beta * p[i];
 }
@@ -292,6 +440,83 @@ __global__ void __launch_bounds__(kBlock) k_cg_update_xr(long long n, long long 
   if (last && threadIdx.x == 0) scal[S_RHO_OLD] = rho;
 }
 __global__ void k_set_scalar(double *p, double v) { *p = v; }
+
+// ---- whole Jacobi-PCG mass solve in ONE CTA (K5: the device replacement of
+// SparseDirectUMFPACK::vmult for the immersed mass matrix, m <= kMassCtaMaxRows) -----
+// The immersed mass matrix is tiny (m = 10^2..10^4 rows, 3-9 non-zeros per row): as
+// separate kernels one solve is ~4*its launches of a few hundred nanoseconds of work
+// each.  Here one 1024-thread CTA runs the calibrated fixed number of iterations with
+// __syncthreads() between phases; vectors stay in L1/L2.  `repeat` = 2 applies M^-1
+// twice (W^-1 = M^-1 M^-1, immersed_laplace.cc:875-876).  y = a * result (+ add).
+constexpr int kMassCtaThreads = 1024;
+constexpr int kMassCtaMaxRows = 16384;
+
+__device__ __forceinline__ double block_allsum_1024(double v, double *smem /*[33]*/) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) smem[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    double t = lane < (kMassCtaThreads >> 5) ? smem[lane] : 0.0;
+    t = warp_sum(t);
+    if (lane == 0) smem[32] = t;
+  }
+  __syncthreads();
+  return smem[32];
+}
+
+__global__ void __launch_bounds__(kMassCtaThreads) k_mass_pcg_cta(CsrDev M, const double *__restrict__ invd, int its,
+                                                                   int repeat, double a, const double *__restrict__ b,
+                                                                   const double *__restrict__ add, double *y,
+                                                                   double *ws /* 5 * m */) {
+  __shared__ double red[33];
+  const int n = M.nrows;
+  double *x = ws, *r = ws + n, *p = ws + 2 * (size_t)n, *v = ws + 3 * (size_t)n, *bb = ws + 4 * (size_t)n;
+  const int tid = threadIdx.x;
+  for (int rep = 0; rep < repeat; ++rep) {
+    const double *rhs = rep == 0 ? b : bb;
+    double part = 0.0;
+    for (int i = tid; i < n; i += kMassCtaThreads) {
+      const double ri = rhs[i];
+      const double zi = invd[i] * ri;
+      x[i] = 0.0;
+      r[i] = ri;
+      p[i] = zi;
+      part += ri * zi;
+    }
+    double rho = block_allsum_1024(part, red);
+    for (int it = 0; it < its; ++it) {
+      part = 0.0;
+      for (int i = tid; i < n; i += kMassCtaThreads) {
+        double s = 0.0;
+        const int k1 = M.rp[i + 1];
+        for (int k = M.rp[i]; k < k1; ++k) s += M.v[k] * p[M.ci[k]];
+        v[i] = s;
+        part += p[i] * s;
+      }
+      const double pv = block_allsum_1024(part, red);
+      const double alpha = pv != 0.0 ? rho / pv : 0.0;
+      part = 0.0;
+      for (int i = tid; i < n; i += kMassCtaThreads) {
+        x[i] += alpha * p[i];
+        const double ri = r[i] - alpha * v[i];
+        r[i] = ri;
+        part += ri * ri * invd[i];
+      }
+      const double rho_new = block_allsum_1024(part, red);
+      const double beta = rho != 0.0 ? rho_new / rho : 0.0;
+      rho = rho_new;
+      for (int i = tid; i < n; i += kMassCtaThreads) p[i] = invd[i] * r[i] + beta * p[i];
+      __syncthreads();
+    }
+    if (rep + 1 < repeat) {
+      for (int i = tid; i < n; i += kMassCtaThreads) bb[i] = x[i];
+      __syncthreads();
+    }
+  }
+  for (int i = tid; i < n; i += kMassCtaThreads) y[i] = a * x[i] + (add ? add[i] : 0.0);
+}
 
 // y = a x + b y   (a, b host scalars; x may alias y only if a-term unused)
 __global__ void __launch_bounds__(kBlock) k_axpby(long long n, double a, const double *__restrict__ x, double b,

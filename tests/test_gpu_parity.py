@@ -133,9 +133,13 @@ def test_full_solve(name, oracle_mod):
     assert ig.kernel_launches > 0
     if ig.outer_iterations == io.outer_iterations:
         err = P.relerr(xg, xo)
+        # 1e-10 unless the oracle itself cannot reproduce its own solution that well under a
+        # one-ulp perturbation of the right-hand side (unstable inner CG trajectories, see
+        # _self_sensitivity)
+        tol = max(TOL_SOLUTION, 50 * _self_sensitivity(lambda v: ora.solve(v)[0], rhs, 4))
         print(f"{name}: outer {ig.outer_iterations}/{io.outer_iterations} inner {ig.inner_iterations}/"
-              f"{io.inner_iterations} solution relerr {err:.3e}")
-        assert err < TOL_SOLUTION
+              f"{io.inner_iterations} solution relerr {err:.3e} (tol {tol:.1e})")
+        assert err < tol
     # the computed solution satisfies the system to the outer tolerance
     res = np.linalg.norm(ora.apply_system(xg) - rhs)
     assert res <= 10 * max(prob.config.outer.tol, prob.config.outer.reduce * ig.initial_residual)
@@ -156,3 +160,46 @@ def test_inner_no_convergence_is_reported(oracle_mod):
     with pytest.raises(NoConvergence) as e:
         gpu.solve(P.rhs_of(gpu, p2))
     assert e.value.status == b.ERR_INNER_NO_CONVERGENCE
+
+
+@pytest.mark.parametrize("name", ["laplace_diag", "laplace_exact", "stokes2d_diag", "stokes2d_exact",
+                                  "stokes2d_minres", "elliptic_modified_diag"])
+def test_reference_style_operator_api(name, oracle_mod):
+    """The literal block algebra of augmented_lagrangian_preconditioner.h evaluated with
+    per-vmult C-ABI calls equals the fused device path (fdal_apply_prec)."""
+    from fictitious_domain_al_preconditioners_b200 import operators as op
+
+    prob, gpu, ora = _pair(name, oracle_mod)
+    ops = op.Operators(gpu)
+    cfg = prob.config
+    k = cfg.kind
+    if k == b.KIND_LAPLACE:
+        Pc = op.BlockPreconditionerAugmentedLagrangian(ops.Aug_inv, ops.C, ops.Ct, ops.invW, cfg.gamma)
+    elif k == b.KIND_STOKES:
+        Pc = op.BlockPreconditionerAugmentedLagrangianStokes(ops.Aug_inv, ops.Bt, ops.Ct, ops.invW, ops.Mp_inv,
+                                                             cfg.gamma, cfg.gamma_grad_div)
+    elif k == b.KIND_STOKES_DIAG_MINRES:
+        Pc = op.BlockPreconditionerAugmentedLagrangianDiagonal(ops.Aug_inv, ops.invW, ops.Mp_inv, cfg.gamma,
+                                                               cfg.gamma_grad_div)
+    else:
+        Pc = op.BlockTriangularALPreconditionerModified(ops.C, ops.M, ops.invW, cfg.gamma, ops.A11_aug_inv,
+                                                        ops.A22_aug_inv)
+    u = op.BlockVector(gpu.sizes, P.rand(prob.n_dofs, 21))
+    v1, v2 = op.BlockVector(gpu.sizes), op.BlockVector(gpu.sizes)
+    Pc.vmult(v1, u)
+    Pc.vmult_fused(v2, u)
+    vo, _ = ora.apply_prec(u.data)
+    tol = max(1e-11, 50 * _self_sensitivity(lambda w: ora.apply_prec(w)[0], u.data, 3))
+    assert P.relerr(v1.data, v2.data) < tol
+    assert P.relerr(v1.data, vo) < tol
+    # AA.vmult and the whole solve through the reference-style driver
+    y = op.BlockVector(gpu.sizes)
+    ops.AA.vmult(y, u)
+    assert P.relerr(y.data, ora.apply_system(u.data)) < TOL_APPLY
+    x = op.BlockVector(gpu.sizes)
+    rhs = op.BlockVector(gpu.sizes, P.rhs_of(ora, prob))
+    solver = op.SolverFGMRES()
+    info = solver.solve(ops.AA, x, rhs, Pc)
+    assert info.status == 0
+    xo, io = ora.solve(rhs.data)
+    assert abs(info.outer_iterations - io.outer_iterations) <= 1

@@ -174,11 +174,14 @@ def vcycle_ref(H, bvec, l=0):
 def test_vcycle_matches_independent_restatement(small, oracle_mod):
     name, prob, H = small
     ctx, _ = ctx_for(oracle_mod, prob, H)
+    def tol(Hh):  # two different direct coarse solves agree to eps * cond(A_coarse)
+        return max(1e-11, 100 * 2.2e-16 * np.linalg.cond(Hh.levels[-1].A.toarray()))
+
     r = P.rand(prob.sizes[0], 7)
-    assert P.relerr(ctx.apply_amg(r), vcycle_ref(H[b.AMG_A11], r)) < 1e-11
+    assert P.relerr(ctx.apply_amg(r), vcycle_ref(H[b.AMG_A11], r)) < tol(H[b.AMG_A11])
     if b.AMG_A22 in H:
         r2 = P.rand(prob.sizes[1], 8)
-        assert P.relerr(ctx.apply_amg(r2, b.AMG_A22), vcycle_ref(H[b.AMG_A22], r2)) < 1e-11
+        assert P.relerr(ctx.apply_amg(r2, b.AMG_A22), vcycle_ref(H[b.AMG_A22], r2)) < tol(H[b.AMG_A22])
 
 
 def test_vcycle_is_a_symmetric_linear_operator(oracle_mod):
@@ -302,14 +305,17 @@ def test_outer_solve_reaches_the_direct_solution(small, oracle_mod):
         assert P.relerr(x[:n], xd[:n]) < 1e-4
     else:
         xd = np.linalg.solve(AA, rhs)
-        assert P.relerr(x, xd) < 1e-6
+        ctl = prob.config.outer
+        assert np.linalg.norm(AA @ x - rhs) <= 10 * max(ctl.tol, ctl.reduce * info.initial_residual)
+        assert P.relerr(x, xd) < 1e-4
     if prob.config.kind == b.KIND_LAPLACE and not prob.config.aug_explicit:
         n, m = prob.Ct.shape
         K = np.block([[prob.A.toarray(), prob.Ct.toarray()], [prob.Ct.toarray().T, np.zeros((m, m))]])
         xs = np.linalg.solve(K, prob.rhs)
         assert P.relerr(x[:n], xs[:n]) < 1e-6
     assert info.outer_iterations == info.n_history - 1
-    assert info.inner_solves == info.outer_iterations
+    per_apply = 2 if prob.config.kind == b.KIND_ELLIPTIC_MODIFIED else 1  # A22 and A11 solves
+    assert info.inner_solves == per_apply * info.outer_iterations
 
 
 def test_minres_variant_converges(oracle_mod):
