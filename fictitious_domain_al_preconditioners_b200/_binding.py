@@ -21,6 +21,7 @@ KIND_LAPLACE, KIND_STOKES, KIND_STOKES_DIAG_MINRES = 0, 1, 2
 KIND_ELLIPTIC_IDEAL, KIND_ELLIPTIC_MODIFIED = 3, 4
 
 MAT_A, MAT_A2, MAT_BT, MAT_B, MAT_CT, MAT_C, MAT_M, MAT_MP = range(8)
+MAT_AMG_A, MAT_AMG_P, MAT_AMG_R = 100, 101, 102
 WINV_DIAG, WINV_EXACT_M, WINV_EXACT_M_SQUARED = 0, 1, 2
 MPINV_CG_LUMPED, MPINV_EXACT = 0, 1
 DIAG_W_INV, DIAG_MP_LUMPED_INV = 0, 1
@@ -134,6 +135,7 @@ DEVICE_SIGNATURES = {
         c_int,
         [c_void_p, c_int, c_int, c_int, c_int64, c_int64, _pi32, _pi32, _pi32],
     ),
+    "amg_set_coarse_range": (c_int, [c_void_p, c_int, c_int64, c_int64]),
 }
 # only the oracle has these
 ORACLE_SIGNATURES = {

@@ -106,6 +106,7 @@ class ALContext:
         self._finalized = False
         self.sizes = None
         self.matrices = set()
+        self.rank, self.nranks = 0, 1
 
     # -- lifetime ----------------------------------------------------------
     def close(self):
@@ -173,6 +174,47 @@ class ALContext:
             )
         Av, ka = b.csr_view(levels[-1].A)
         self._check(self.api.amg_set_coarse(self._h, which, len(levels) - 1, C.byref(Av)))
+
+    # -- multi-GPU (one process per GPU) --------------------------------------------
+    def nccl_unique_id(self) -> bytes:
+        buf = (C.c_char * 128)()
+        self._check(self.api.nccl_unique_id(buf))
+        return bytes(buf.raw)
+
+    def comm_init(self, uid: bytes, rank: int, nranks: int):
+        buf = (C.c_char * 128).from_buffer_copy(uid)
+        self._check(self.api.comm_init(self._h, buf, rank, nranks))
+        self.rank, self.nranks = rank, nranks
+
+    def set_halo(self, matrix_id: int, plan, level: int = 0, which: int = 0):
+        i32 = C.POINTER(C.c_int32)
+        sc = np.ascontiguousarray(plan.send_counts, dtype=np.int32)
+        si = np.ascontiguousarray(plan.send_idx, dtype=np.int32)
+        rc = np.ascontiguousarray(plan.recv_counts, dtype=np.int32)
+        if si.size == 0:
+            si = np.zeros(1, dtype=np.int32)
+        self._check(self.api.set_halo(self._h, matrix_id, level, which, plan.n_owned, plan.n_halo,
+                                      sc.ctypes.data_as(i32), si.ctypes.data_as(i32), rc.ctypes.data_as(i32)))
+
+    def set_amg_local(self, which: int, LH):
+        """``LH``: ``partition.LocalHierarchy`` (this rank's rows of every level)."""
+        for l, L in enumerate(LH.levels):
+            Av, ka = b.csr_view(L.A.local)
+            Pv, kp = b.csr_view(L.P.local)
+            Rv, kr = b.csr_view(L.R.local)
+            idg = b.as_f64(L.inv_diag) if L.inv_diag is not None else None
+            self._check(self.api.amg_set_level(
+                self._h, which, l, C.byref(Av), C.byref(Pv), C.byref(Rv),
+                b.dptr(idg) if idg is not None else None, float(L.lambda_max), int(LH.cheb_degree),
+                float(LH.eig_ratio)))
+            for mid, dc in ((b.MAT_AMG_A, L.A), (b.MAT_AMG_P, L.P), (b.MAT_AMG_R, L.R)):
+                if dc.plan is not None:
+                    self.set_halo(mid, dc.plan, level=l, which=which)
+        Av, ka = b.csr_view(LH.coarse_A)
+        nl = len(LH.levels)
+        self._check(self.api.amg_set_coarse(self._h, which, nl, C.byref(Av)))
+        self._check(self.api.amg_set_coarse_range(self._h, which, int(LH.coarse_off[self.rank]),
+                                                  int(LH.coarse_off[self.rank + 1])))
 
     def finalize(self):
         self._check(self.api.finalize(self._h))

@@ -8,6 +8,8 @@
 // back one scalar per inner CG iteration (the residual norm deal.II's SolverControl
 // tests) and the Hessenberg column per outer iteration.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types only: the library is dlopen()ed at fdal_comm_init, never linked
 
 #include <algorithm>
 #include <cmath>
@@ -25,12 +27,57 @@
 
 namespace fdal {
 
+// ------------------------------------------------------------------ NCCL, loaded lazily
+// The single-GPU path has no NCCL dependency.  With several ranks the process usually
+// already holds torch's bundled libnccl.so.2; dlopen() by soname reuses that copy.
+struct NcclApi {
+  void *handle = nullptr;
+  decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+  decltype(&ncclCommInitRank) CommInitRank = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclAllReduce) AllReduce = nullptr;
+  decltype(&ncclSend) Send = nullptr;
+  decltype(&ncclRecv) Recv = nullptr;
+  decltype(&ncclGroupStart) GroupStart = nullptr;
+  decltype(&ncclGroupEnd) GroupEnd = nullptr;
+  decltype(&ncclGetErrorString) GetErrorString = nullptr;
+  bool ok = false;
+};
+static NcclApi *nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return &api;
+  tried = true;
+  api.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!api.handle) api.handle = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!api.handle) return &api;
+#define FDAL_SYM(name) api.name = (decltype(api.name))dlsym(api.handle, "nccl" #name)
+  FDAL_SYM(GetUniqueId);
+  FDAL_SYM(CommInitRank);
+  FDAL_SYM(CommDestroy);
+  FDAL_SYM(AllReduce);
+  FDAL_SYM(Send);
+  FDAL_SYM(Recv);
+  FDAL_SYM(GroupStart);
+  FDAL_SYM(GroupEnd);
+  FDAL_SYM(GetErrorString);
+#undef FDAL_SYM
+  api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.Send && api.Recv &&
+           api.GroupStart && api.GroupEnd;
+  return &api;
+}
+
 // ------------------------------------------------------------------ host CSR
 struct HostCsr {
   int64_t nr = 0, nc = 0, nnz = 0;
   std::vector<int> rp, ci;
   std::vector<double> v;
   bool set = false;
+  // halo plan (multi-GPU): columns [0, n_owned) are owned, [n_owned, n_owned + n_halo) halo
+  bool has_plan = false;
+  int64_t n_owned = 0, n_halo = 0;
+  std::vector<int> send_counts, recv_counts, send_idx;
+  int64_t owned_cols() const { return has_plan ? n_owned : nc; }
 };
 static void host_transpose(const HostCsr &A, HostCsr &T) {
   // stable counting sort: within a row of T columns ascend, i.e. the same
@@ -62,6 +109,13 @@ struct DevCsr {
   int4 *desc = nullptr;
   int nblk = 0;
   bool stream_ok = false;
+  // multi-GPU
+  bool dist_rows = false;  // rows are a partition: fused reductions need an all-reduce
+  bool has_plan = false;
+  int n_owned = std::numeric_limits<int>::max(), n_halo = 0, n_send = 0;
+  double *halo_buf = nullptr, *send_buf = nullptr;
+  int *send_idx = nullptr;
+  std::vector<int> send_counts, recv_counts;
 };
 
 struct AmgLevel {
@@ -76,7 +130,11 @@ struct AmgLevel {
 };
 struct Amg {
   std::vector<AmgLevel> lev;
-  double *cinv = nullptr;
+  double *cinv = nullptr;   // dense inverse of the (replicated) coarsest operator
+  double *cfull = nullptr;  // replicated coarse right-hand side (multi-GPU)
+  int cn_global = 0;        // rows of the coarsest operator
+  int64_t c_lo = 0, c_hi = -1;  // rows of it owned by this rank
+  bool dist = false;
   bool ready = false;
 };
 
@@ -110,6 +168,8 @@ struct CgWs {
   double *x = nullptr;     // the iterate lives here so the iteration body is pointer-stable
   double *bin = nullptr;   // staged right-hand side of the fixed-count mass solve
   double *scal = nullptr;  // S_COUNT device scalars
+  bool dist = false;       // vector is partitioned: dots need an all-reduce
+  int64_t n_dot = 0;       // entries this rank contributes to dots (replicated tail counted on rank 0)
   // CUDA graphs: one iteration body (host-checked CG) / one whole fixed-count solve
   cudaGraphExec_t body_exec = nullptr, fixed_exec = nullptr;
   int64_t body_nodes = 0, fixed_nodes = 0;
@@ -152,8 +212,12 @@ struct fdal_ctx {
   // counters
   int its_a11 = 0, its_a22 = 0, its_mass = 0, n_inner_solves = 0;
   int64_t launches = 0, graph_launches = 0;
-  int stream_ctas_per_sm = 4, spmv_unroll = 1;
-  bool prefer_stream = true;
+  // multi-GPU
+  int rank = 0, nranks = 1;
+  ncclComm_t comm = nullptr;
+  int64_t n_dot_outer = 0;
+  int stream_ctas_per_sm = 3, spmv_unroll = 4;
+  bool prefer_stream = false;
   int fail = 0;
   std::vector<void *> allocs;
   std::string err;
@@ -203,11 +267,12 @@ static int choose_tpr(double avg) {
     int t = atoi(env);
     if (t == 2 || t == 4 || t == 8 || t == 16 || t == 32) return t;
   }
-  if (avg <= 2.5) return 2;
-  if (avg <= 6.0) return 4;
-  if (avg <= 14.0) return 8;
-  if (avg <= 40.0) return 16;
-  return 32;
+  // ~4 non-zeros per lane (measured on B200: more rows per warp = more independent
+  // load chains; see profiles/)
+  if (avg <= 12.0) return 2;
+  if (avg <= 24.0) return 4;
+  if (avg <= 96.0) return 8;
+  return 16;
 }
 
 static int upload_csr(fdal_ctx *c, const HostCsr &h, DevCsr &d) {
@@ -236,6 +301,21 @@ static int upload_csr(fdal_ctx *c, const HostCsr &h, DevCsr &d) {
   d.d.v = d.v;
   d.d.tpr = choose_tpr(h.nr ? (double)h.nnz / (double)h.nr : 1.0);
   d.set = true;
+  if (h.has_plan) {
+    d.has_plan = true;
+    d.n_owned = (int)h.n_owned;
+    d.n_halo = (int)h.n_halo;
+    d.n_send = (int)h.send_idx.size();
+    d.send_counts = h.send_counts;
+    d.recv_counts = h.recv_counts;
+    if ((st = dvec(c, &d.halo_buf, d.n_halo))) return st;
+    if ((st = dvec(c, &d.send_buf, d.n_send))) return st;
+    if ((st = dmalloc(c, &d.send_idx, (size_t)d.n_send))) return st;
+    if (d.n_send)
+      CU(cudaMemcpyAsync(d.send_idx, h.send_idx.data(), (size_t)d.n_send * sizeof(int), cudaMemcpyHostToDevice,
+                         c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
   // chunk plan: runs of whole rows whose 4-aligned non-zero range fits kChunk
   {
     const bool no_stream = getenv("FDAL_NO_STREAM") != nullptr;
@@ -272,14 +352,40 @@ static inline int grid_elems(const fdal_ctx *c, long long n) {
   return (int)std::max<long long>(1, std::min<long long>(g, (long long)c->sms * kMaxGridPerSM));
 }
 static inline Reducer reducer(fdal_ctx *c, double *out) { return Reducer{c->d_partials, c->d_counter, out}; }
-static inline XVec xv(const double *x) { return XVec{x, nullptr, std::numeric_limits<int>::max()}; }
+
+// sum of device doubles over all ranks, in stream order (NVLink / NVSwitch through NCCL)
+static void allreduce(fdal_ctx *c, double *p, size_t count) {
+  if (c->nranks <= 1 || !count) return;
+  ncclResult_t r = nccl_api()->AllReduce(p, p, count, ncclDouble, ncclSum, c->comm, c->stream);
+  if (r != ncclSuccess && !c->fail) c->fail = FDAL_ERR_NCCL;
+}
+// fill A's halo buffer with the owners' entries of x: pack -> grouped send/recv
+static void halo_exchange(fdal_ctx *c, const DevCsr &A, const double *x) {
+  if (!A.has_plan || c->nranks <= 1) return;
+  if (A.n_send) {
+    k_pack<<<grid_elems(c, A.n_send), kBlock, 0, c->stream>>>(A.n_send, A.send_idx, x, A.send_buf);
+    c->launches++;
+  }
+  NcclApi *n = nccl_api();
+  n->GroupStart();
+  size_t so = 0, ro = 0;
+  for (int q = 0; q < c->nranks; ++q) {
+    if (A.send_counts[q]) n->Send(A.send_buf + so, (size_t)A.send_counts[q], ncclDouble, q, c->comm, c->stream);
+    if (A.recv_counts[q]) n->Recv(A.halo_buf + ro, (size_t)A.recv_counts[q], ncclDouble, q, c->comm, c->stream);
+    so += (size_t)A.send_counts[q];
+    ro += (size_t)A.recv_counts[q];
+  }
+  ncclResult_t r = n->GroupEnd();
+  if (r != ncclSuccess && !c->fail) c->fail = FDAL_ERR_NCCL;
+}
+static inline XVec xv(const DevCsr &A, const double *x) { return XVec{x, A.halo_buf, A.n_owned}; }
 
 template <class Epi, bool TWO>
 static void spmv_stream(fdal_ctx *c, const DevCsr &A, const double *x, const DevCsr *B2, const double *t2, Epi epi,
                         double *red_out) {
   const int g = std::max(1, std::min(A.nblk, c->sms * c->stream_ctas_per_sm));
   Reducer R = reducer(c, red_out);
-  XVec X = xv(x);
+  XVec X = xv(A, x);
   StreamPlan plan{A.desc, A.nblk};
   CsrDev b2 = B2 ? B2->d : CsrDev();
   const size_t sm = kStreamSmemBytes;
@@ -300,17 +406,25 @@ static void spmv_stream(fdal_ctx *c, const DevCsr &A, const double *x, const Dev
     default: k_spmv_stream<32, Epi, TWO><<<g, kBlock, sm, c->stream>>>(A.d, plan, X, b2, t2, epi, R); break;
   }
   c->launches++;
+  if (red_out && A.dist_rows) allreduce(c, red_out, 1);
 }
 template <class Epi>
 static void spmv(fdal_ctx *c, const DevCsr &A, const double *x, Epi epi, double *red_out = nullptr) {
-  if (A.d.nrows == 0) return;
+  halo_exchange(c, A, x);
+  if (A.d.nrows == 0) {
+    if (red_out) {
+      cudaMemsetAsync(red_out, 0, sizeof(double), c->stream);
+      if (A.dist_rows) allreduce(c, red_out, 1);
+    }
+    return;
+  }
   if (A.stream_ok && c->prefer_stream) {
     spmv_stream<Epi, false>(c, A, x, nullptr, nullptr, epi, red_out);
     return;
   }
   const int g = grid_rows(c, A.d.nrows, A.d.tpr);
   Reducer R = reducer(c, red_out);
-  XVec X = xv(x);
+  XVec X = xv(A, x);
   if (c->spmv_unroll > 1) {
     switch (A.d.tpr) {
       case 2: k_spmv<2, Epi, 4><<<g, kBlock, 0, c->stream>>>(A.d, X, epi, R); break;
@@ -329,18 +443,26 @@ static void spmv(fdal_ctx *c, const DevCsr &A, const double *x, Epi epi, double 
     }
   }
   c->launches++;
+  if (red_out && A.dist_rows) allreduce(c, red_out, 1);
 }
 template <class Epi>
 static void spmv2(fdal_ctx *c, const DevCsr &A, const double *x, const DevCsr &Ct, const double *t, Epi epi,
                   double *red_out = nullptr) {
-  if (A.d.nrows == 0) return;
+  halo_exchange(c, A, x);
+  if (A.d.nrows == 0) {
+    if (red_out) {
+      cudaMemsetAsync(red_out, 0, sizeof(double), c->stream);
+      if (A.dist_rows) allreduce(c, red_out, 1);
+    }
+    return;
+  }
   if (A.stream_ok && c->prefer_stream) {
     spmv_stream<Epi, true>(c, A, x, &Ct, t, epi, red_out);
     return;
   }
   const int g = grid_rows(c, A.d.nrows, A.d.tpr);
   Reducer R = reducer(c, red_out);
-  XVec X = xv(x);
+  XVec X = xv(A, x);
   if (c->spmv_unroll > 1) {
     switch (A.d.tpr) {
       case 2: k_spmv2<2, Epi, 4><<<g, kBlock, 0, c->stream>>>(A.d, X, Ct.d, t, epi, R); break;
@@ -359,10 +481,13 @@ static void spmv2(fdal_ctx *c, const DevCsr &A, const double *x, const DevCsr &C
     }
   }
   c->launches++;
+  if (red_out && A.dist_rows) allreduce(c, red_out, 1);
 }
-static void dot(fdal_ctx *c, int64_t n, const double *a, const double *b, double *out) {
-  k_dot<<<grid_elems(c, n), kBlock, 0, c->stream>>>(n, a, b, reducer(c, out));
+// out = a[0:n) . b[0:n); dist: n is this rank's share, all-reduced over the ranks
+static void dot(fdal_ctx *c, int64_t n, const double *a, const double *b, double *out, bool dist = false) {
+  k_dot<<<grid_elems(c, std::max<int64_t>(n, 1)), kBlock, 0, c->stream>>>(n, a, b, reducer(c, out));
   c->launches++;
+  if (dist) allreduce(c, out, 1);
 }
 static void axpby(fdal_ctx *c, int64_t n, double a, const double *x, double b, double *y) {
   if (n == 0) return;
@@ -441,14 +566,29 @@ static double *cheb(fdal_ctx *c, AmgLevel &L, const double *b, double *xcur, boo
   }
   return cur;
 }
+// coarsest level: x = A_L^-1 b.  Multi-GPU: the right-hand side is all-reduced into a
+// replicated vector and every rank applies its rows of the replicated inverse.
+static void coarse_solve(fdal_ctx *c, Amg &g, const double *b_local, double *x_local) {
+  AmgLevel &C = g.lev.back();
+  const double *rhs = b_local;
+  if (g.dist) {
+    dzero(c, g.cn_global, g.cfull);
+    dcopy(c, C.n, b_local, g.cfull + g.c_lo);
+    allreduce(c, g.cfull, (size_t)g.cn_global);
+    rhs = g.cfull;
+  }
+  if (C.n > 0) {
+    k_gemv<<<(C.n * 32 + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(C.n, g.cn_global,
+                                                                       g.cinv + (size_t)g.c_lo * g.cn_global, rhs, x_local);
+    c->launches++;
+  }
+}
 // z = AMG(b); optionally *red_out = b.z
 static void vcycle(fdal_ctx *c, Amg &g, const double *b0, double *z, double *red_out) {
   const int nl = (int)g.lev.size();
   if (nl == 1) {
-    const int n = g.lev[0].n;
-    k_gemv<<<(n * 32 + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(n, g.cinv, b0, z);
-    c->launches++;
-    if (red_out) dot(c, n, b0, z, red_out);
+    coarse_solve(c, g, b0, z);
+    if (red_out) dot(c, g.lev[0].n, b0, z, red_out, g.dist);
     return;
   }
   std::vector<double *> xres(nl, nullptr);
@@ -462,8 +602,7 @@ static void vcycle(fdal_ctx *c, Amg &g, const double *b0, double *z, double *red
   }
   {
     AmgLevel &C = g.lev[nl - 1];
-    k_gemv<<<(C.n * 32 + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(C.n, g.cinv, C.b, C.xa);
-    c->launches++;
+    coarse_solve(c, g, C.b, C.xa);
     xres[nl - 1] = C.xa;
   }
   for (int l = nl - 2; l >= 0; --l) {
@@ -491,9 +630,10 @@ static void cg_body(fdal_ctx *c, CgWs &w, const OpFn &op, const OpFn &prec, doub
   k_cg_update_p<<<grid_elems(c, n), kBlock, 0, c->stream>>>(n, w.z, w.p, w.scal);
   c->launches++;
   op(w.p, w.v, w.scal + S_PV);
-  k_cg_update_xr<<<grid_elems(c, n), kBlock, 0, c->stream>>>(n, n, w.p, w.v, x, w.r, w.scal,
+  k_cg_update_xr<<<grid_elems(c, n), kBlock, 0, c->stream>>>(n, w.dist ? w.n_dot : n, w.p, w.v, x, w.r, w.scal,
                                                                reducer(c, w.scal + S_RR));
   c->launches++;
+  if (w.dist) allreduce(c, w.scal + S_RR, 1);
 }
 static bool stream_is_capturing(fdal_ctx *c) {
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
@@ -526,8 +666,13 @@ static bool capture_graph(fdal_ctx *c, const std::function<void()> &enqueue, cud
   }
   return true;
 }
+static bool graphs_enabled(const fdal_ctx *c) {
+  // NCCL calls can be captured, but keep the multi-rank path on plain launches unless asked
+  static const bool dist_graphs = getenv("FDAL_DIST_GRAPHS") != nullptr;
+  return c->cfg.use_graphs && (c->nranks <= 1 || dist_graphs);
+}
 static void run_cg_body(fdal_ctx *c, CgWs &w, const OpFn &op, const OpFn &prec, bool capturable) {
-  if (c->cfg.use_graphs && capturable && w.graph_ok && !stream_is_capturing(c)) {
+  if (graphs_enabled(c) && capturable && w.graph_ok && !stream_is_capturing(c)) {
     if (!w.body_exec)
       w.graph_ok = capture_graph(c, [&]() { cg_body(c, w, op, prec, w.x); }, &w.body_exec, &w.body_nodes);
     if (w.body_exec) {
@@ -547,7 +692,7 @@ static int cg_solve(fdal_ctx *c, CgWs &w, const OpFn &op, const OpFn &prec, cons
   ControlState cs;
   cs.c = ctl;
   cg_start(c, w, b, w.x);
-  dot(c, w.n, w.r, w.r, w.scal + S_RR);
+  dot(c, w.dist ? w.n_dot : w.n, w.r, w.r, w.scal + S_RR, w.dist);
   double rr;
   int st = read_scalars(c, w.scal + S_RR, 1, &rr);
   if (st) return st;
@@ -566,21 +711,24 @@ static int cg_solve(fdal_ctx *c, CgWs &w, const OpFn &op, const OpFn &prec, cons
 }
 // fixed-count Jacobi-PCG on a mass matrix: the device replacement of
 // SparseDirectUMFPACK::vmult (K5); no host interaction
-static void mass_prec(fdal_ctx *c, const double *invdiag, int64_t n, const double *r, double *z, double *dot_out) {
-  k_diag_prec_dot<<<grid_elems(c, n), kBlock, 0, c->stream>>>(n, invdiag, r, z, reducer(c, dot_out));
+static void mass_prec(fdal_ctx *c, const double *invdiag, int64_t n, const double *r, double *z, double *dot_out,
+                      bool dist = false) {
+  k_diag_prec_dot<<<grid_elems(c, std::max<int64_t>(n, 1)), kBlock, 0, c->stream>>>(n, invdiag, r, z,
+                                                                                   reducer(c, dot_out));
   c->launches++;
+  if (dist) allreduce(c, dot_out, 1);
 }
 static void mass_solve_fixed(fdal_ctx *c, CgWs &w, const DevCsr &M, const double *invdiag, int its, const double *b,
                              double *x) {
   OpFn op = [&](const double *in, double *out, double *d) { spmv(c, M, in, EpiDotX{out, in}, d); };
-  OpFn pr = [&](const double *r, double *z, double *d) { mass_prec(c, invdiag, w.n, r, z, d); };
+  OpFn pr = [&](const double *r, double *z, double *d) { mass_prec(c, invdiag, w.n, r, z, d, w.dist); };
   auto whole = [&]() {
     cg_start(c, w, w.bin, w.x);
     for (int i = 0; i < its; ++i) cg_body(c, w, op, pr, w.x);
   };
   dcopy(c, w.n, b, w.bin);
   bool done = false;
-  if (c->cfg.use_graphs && w.graph_ok && !stream_is_capturing(c)) {
+  if (graphs_enabled(c) && w.graph_ok && !stream_is_capturing(c)) {
     if (!w.fixed_exec) w.graph_ok = capture_graph(c, whole, &w.fixed_exec, &w.fixed_nodes);
     if (w.fixed_exec) {
       cudaGraphLaunch(w.fixed_exec, c->stream);
@@ -606,11 +754,11 @@ static int mass_calibrate(fdal_ctx *c, CgWs &w, const DevCsr &M, const double *i
   int st;
   CU(cudaMemcpyAsync(b, hb.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   cg_start(c, w, b, x);
-  dot(c, n, w.r, w.r, w.scal + S_RR);
+  dot(c, n, w.r, w.r, w.scal + S_RR, w.dist);
   double rr0;
   if ((st = read_scalars(c, w.scal + S_RR, 1, &rr0))) return st;
   OpFn op = [&](const double *in, double *out, double *d) { spmv(c, M, in, EpiDotX{out, in}, d); };
-  OpFn pr = [&](const double *r, double *z, double *d) { mass_prec(c, invdiag, n, r, z, d); };
+  OpFn pr = [&](const double *r, double *z, double *d) { mass_prec(c, invdiag, n, r, z, d, w.dist); };
   const int cap = c->cfg.exact_mass_max_its > 0 ? c->cfg.exact_mass_max_its : 300;
   int it = 0;
   double rr = rr0;
@@ -663,7 +811,9 @@ static int apply_mp_inv(fdal_ctx *c, const double *x, double *y) {
     return FDAL_OK;
   }
   OpFn op = [&](const double *in, double *out, double *d) { spmv(c, c->dmat[FDAL_MAT_MP], in, EpiDotX{out, in}, d); };
-  OpFn pr = [&](const double *r, double *z, double *d) { mass_prec(c, c->d_mp_lumped, c->n1, r, z, d); };
+  OpFn pr = [&](const double *r, double *z, double *d) {
+    mass_prec(c, c->d_mp_lumped, c->n1, r, z, d, c->cgmass_p.dist);
+  };
   int its = 0;
   int st = cg_solve(c, c->cgmass_p, op, pr, c->cfg.mass, x, y, &its, FDAL_ERR_MASS_NO_CONVERGENCE, true);
   c->its_mass += its;
@@ -674,6 +824,20 @@ static int apply_mp_inv(fdal_ctx *c, const double *x, double *y) {
 // phase 1 of the fused augmented apply: t = a * invW (C x [- M x1m]) + add ; y1 = C x
 static void couple_phase1(fdal_ctx *c, const double *x, double a, const double *add, double *y1, double *t) {
   const DevCsr &C = c->dmat[FDAL_MAT_C];
+  if (c->nranks > 1) {
+    // C holds this rank's columns: partial sums, all-reduced over the m multiplier rows
+    double *w = (y1 && c->cfg.winv_mode != FDAL_WINV_DIAG) ? y1 : c->t_m1;
+    spmv(c, C, x, EpiAssign{w, 1.0});
+    allreduce(c, w, (size_t)c->m);
+    if (c->cfg.winv_mode == FDAL_WINV_DIAG) {
+      k_couple_elem<<<grid_elems(c, c->m), kBlock, 0, c->stream>>>((int)c->m, w, c->d_winv, a, add, y1, t);
+      c->launches++;
+    } else {
+      if (y1 && w != y1) dcopy(c, c->m, w, y1);
+      apply_winv_scaled(c, a, w, t, add);
+    }
+    return;
+  }
   if (c->cfg.winv_mode == FDAL_WINV_DIAG) {
     spmv(c, C, x, EpiCouple{t, c->d_winv, a, add, y1});
   } else {
@@ -702,7 +866,7 @@ static void apply_aug11(fdal_ctx *c, const double *x, double *y, double *dot_out
     spmv(c, c->dmat[FDAL_MAT_B], x, EpiAssign{c->t_p0, 1.0});
     apply_mp_inv(c, c->t_p0, c->t_p1);
     spmv(c, c->dmat[FDAL_MAT_BT], c->t_p1, EpiAdd{y, c->cfg.gamma_grad_div});
-    if (dot_out) dot(c, c->n0, x, y, dot_out);
+    if (dot_out) dot(c, c->n0, x, y, dot_out, c->nranks > 1);
   }
 }
 // A22_aug = A2 + gamma_2 M invW M (elliptic_interface.cc:810)
@@ -731,6 +895,7 @@ static void apply_aug(fdal_ctx *c, int which, const double *x, double *y, double
 // (the four LinearOperator blocks of elliptic_interface.cc:807-813 share tw)
 static void elliptic_w(fdal_ctx *c, const double *x0, const double *x1, double *w) {
   spmv(c, c->dmat[FDAL_MAT_C], x0, EpiAssign{w, 1.0});
+  allreduce(c, w, (size_t)c->m);
   spmv(c, c->dmat[FDAL_MAT_M], x1, EpiAdd{w, -1.0});
 }
 static void apply_aug_block(fdal_ctx *c, const double *x, double *y, double *dot_out) {
@@ -742,7 +907,7 @@ static void apply_aug_block(fdal_ctx *c, const double *x, double *y, double *dot
   spmv2(c, c->dmat[FDAL_MAT_A], x0, c->dmat[FDAL_MAT_CT], c->t_m0, EpiAssign{y0, 1.0});
   axpby(c, c->m, -c->cfg.gamma2, c->t_m2, 0.0, c->t_m0);
   spmv2(c, c->dmat[FDAL_MAT_A2], x1, c->dmat[FDAL_MAT_M], c->t_m0, EpiAssign{y1, 1.0});
-  if (dot_out) dot(c, c->n0 + c->n1, x, y, dot_out);
+  if (dot_out) dot(c, c->cgblk.dist ? c->cgblk.n_dot : c->n0 + c->n1, x, y, dot_out, c->cgblk.dist);
 }
 
 // AA.vmult / system_operator.vmult (a7)
@@ -755,6 +920,7 @@ static void apply_system(fdal_ctx *c, const double *x, double *y) {
       // y0 = A x0 + Ct (gamma invW C x0 + x1) ; y1 = C x0
       if (c->cfg.aug_explicit) {
         spmv(c, c->dmat[FDAL_MAT_C], x0, EpiAssign{y1, 1.0});
+        allreduce(c, y1, (size_t)c->m);
         spmv2(c, A, x0, Ct, x1, EpiAssign{y0, 1.0});
       } else {
         couple_phase1(c, x0, c->cfg.gamma, x1, y1, c->t_m0);
@@ -765,6 +931,7 @@ static void apply_system(fdal_ctx *c, const double *x, double *y) {
     case FDAL_KIND_STOKES_DIAG_MINRES:
       if (c->cfg.aug_explicit) {
         spmv(c, c->dmat[FDAL_MAT_C], x0, EpiAssign{y2, 1.0});
+        allreduce(c, y2, (size_t)c->m);
         spmv2(c, A, x0, Ct, x2, EpiAssign{y0, 1.0});
       } else {
         couple_phase1(c, x0, c->cfg.gamma, x2, y2, c->t_m0);
@@ -802,7 +969,7 @@ static int apply_aug_inv(fdal_ctx *c, int which, const double *b, double *x, int
   else
     pr = [c, &w](const double *r, double *z, double *d) {
       dcopy(c, w.n, r, z);
-      dot(c, w.n, r, z, d);
+      dot(c, w.dist ? w.n_dot : w.n, r, z, d, w.dist);
     };
   // the only non-capturable body: the no-grad-div Stokes operator nests a host-checked Mp CG
   const bool capturable = !(which == FDAL_AMG_A11 && is_stokes(c) && c->cfg.grad_div_in_operator &&
@@ -856,12 +1023,12 @@ static int apply_prec(fdal_ctx *c, const double *u, double *v) {
         pr = [c](const double *r, double *z, double *d) {
           vcycle(c, c->amg[0], r, z, nullptr);
           vcycle(c, c->amg[1], r + c->n0, z + c->n0, nullptr);
-          dot(c, c->n0 + c->n1, r, z, d);
+          dot(c, c->cgblk.dist ? c->cgblk.n_dot : c->n0 + c->n1, r, z, d, c->cgblk.dist);
         };
       else
         pr = [c](const double *r, double *z, double *d) {
           dcopy(c, c->n0 + c->n1, r, z);
-          dot(c, c->n0 + c->n1, r, z, d);
+          dot(c, c->cgblk.dist ? c->cgblk.n_dot : c->n0 + c->n1, r, z, d, c->cgblk.dist);
         };
       int st = cg_solve(c, c->cgblk, op, pr, c->cfg.inner, uu, v, &its, FDAL_ERR_INNER_NO_CONVERGENCE, true);
       c->its_a11 += its;
@@ -899,6 +1066,8 @@ static void record(fdal_solve_info *info, double res) {
 // re-orthogonalisation pass; Hessenberg / Givens on the host (O(restart^2)).
 static int fgmres(fdal_ctx *c, const double *b, double *x, fdal_solve_info *info) {
   const int64_t N = c->N;
+  const int64_t Nd = c->n_dot_outer;  // entries this rank contributes to dots
+  const bool dist = c->nranks > 1;
   const int mb = c->cfg.restart;
   std::vector<double> H((size_t)(mb + 1) * mb, 0.0), g(mb + 1), cs(mb), sn(mb), y(mb), hh(2 * (mb + 2));
   ControlState ctl;
@@ -909,7 +1078,7 @@ static int fgmres(fdal_ctx *c, const double *b, double *x, fdal_solve_info *info
   do {
     apply_system(c, x, Vj(0));
     axpby(c, N, 1.0, b, -1.0, Vj(0));
-    dot(c, N, Vj(0), Vj(0), c->d_scal);
+    dot(c, Nd, Vj(0), Vj(0), c->d_scal, dist);
     double rr;
     if ((st = read_scalars(c, c->d_scal, 1, &rr))) return st;
     double res = std::sqrt(rr);
@@ -932,11 +1101,13 @@ static int fgmres(fdal_ctx *c, const double *b, double *x, fdal_solve_info *info
       const int nv = j + 1;
       double *h1 = c->d_h, *h2 = c->d_h + (mb + 2);
       const int gd = grid_elems(c, N);
-      k_multidot<<<gd, kBlock, 0, c->stream>>>(N, N, w, c->V, N, nv, 0, reducer(c, h1));
+      k_multidot<<<gd, kBlock, 0, c->stream>>>(N, Nd, w, c->V, N, nv, 0, reducer(c, h1));
+      if (dist) allreduce(c, h1, (size_t)nv);
       k_multiaxpy<<<gd, kBlock, 0, c->stream>>>(N, w, c->V, N, nv, h1, -1.0);
-      k_multidot<<<gd, kBlock, 0, c->stream>>>(N, N, w, c->V, N, nv, 0, reducer(c, h2));
+      k_multidot<<<gd, kBlock, 0, c->stream>>>(N, Nd, w, c->V, N, nv, 0, reducer(c, h2));
+      if (dist) allreduce(c, h2, (size_t)nv);
       k_multiaxpy<<<gd, kBlock, 0, c->stream>>>(N, w, c->V, N, nv, h2, -1.0);
-      dot(c, N, w, w, h2 + nv);
+      dot(c, Nd, w, w, h2 + nv, dist);
       k_scale_by_inv<<<gd, kBlock, 0, c->stream>>>(N, w, h2 + nv, 1, w);
       c->launches += 5;
       // one read-back per outer iteration: h1[0..nv), h2[0..nv], |w|^2
@@ -994,7 +1165,7 @@ static int minres(fdal_ctx *c, const double *b, double *x, fdal_solve_info *info
   ctl.c = c->cfg.outer;
   int j = 1, st;
   auto hdot = [&](const double *a, const double *bb, double *out) -> int {
-    dot(c, N, a, bb, c->d_scal);
+    dot(c, c->n_dot_outer, a, bb, c->d_scal, c->nranks > 1);
     return read_scalars(c, c->d_scal, 1, out);
   };
   apply_system(c, x, m[0]);
@@ -1066,7 +1237,7 @@ static int minres(fdal_ctx *c, const double *b, double *x, fdal_solve_info *info
 // ------------------------------------------------------------------ finalize helpers
 static int invert_coarse(fdal_ctx *c, Amg &g) {
   AmgLevel &C = g.lev.back();
-  const int n = C.n;
+  const int n = g.cn_global;  // the coarsest operator is replicated on every rank
   double *aug = nullptr, *col = nullptr, *pval = nullptr;
   int *prow = nullptr, *sing = nullptr;
   int st;
@@ -1101,30 +1272,51 @@ static int invert_coarse(fdal_ctx *c, Amg &g) {
   return FDAL_OK;
 }
 
-static int prepare_amg(fdal_ctx *c, Amg &g) {
+static int prepare_amg(fdal_ctx *c, Amg &g, bool dist) {
   int st;
   const int nl = (int)g.lev.size();
+  g.dist = dist;
   for (int l = 0; l < nl; ++l) {
     AmgLevel &L = g.lev[l];
     if (!L.hA.set) {
       set_err(c, "AMG level %d was never set", l);
       return FDAL_ERR_STATE;
     }
-    L.n = (int)L.hA.nr;
+    const bool coarsest = (l == nl - 1);
+    if (coarsest) {
+      g.cn_global = (int)L.hA.nr;
+      if (!dist || g.c_hi < 0) {
+        g.c_lo = 0;
+        g.c_hi = L.hA.nr;
+      }
+      L.n = (int)(g.c_hi - g.c_lo);
+    } else {
+      L.n = (int)L.hA.nr;
+    }
     if ((st = upload_csr(c, L.hA, L.A))) return st;
-    if (l < nl - 1) {
+    L.A.dist_rows = dist;
+    if (!coarsest) {
       if (!L.hP.set) {
         set_err(c, "AMG level %d has no prolongator", l);
         return FDAL_ERR_STATE;
       }
-      if (L.hP.nc != g.lev[l + 1].hA.nr) {
-        set_err(c, "AMG level %d: P has %lld columns, next level has %lld rows", l, (long long)L.hP.nc,
-                (long long)g.lev[l + 1].hA.nr);
+      const AmgLevel &Nx = g.lev[l + 1];
+      const int64_t next_rows = (l + 1 == nl - 1 && dist && g.c_hi >= 0) ? (g.c_hi - g.c_lo) : Nx.hA.nr;
+      if (L.hP.owned_cols() != next_rows) {
+        set_err(c, "AMG level %d: P has %lld owned columns, next level has %lld rows", l,
+                (long long)L.hP.owned_cols(), (long long)next_rows);
         return FDAL_ERR_SHAPE;
       }
       if ((st = upload_csr(c, L.hP, L.P))) return st;
-      if (!L.hR.set) host_transpose(L.hP, L.hR);
+      if (!L.hR.set) {
+        if (dist) {
+          set_err(c, "AMG level %d: a partitioned hierarchy needs an explicit R with its halo plan", l);
+          return FDAL_ERR_STATE;
+        }
+        host_transpose(L.hP, L.hR);
+      }
       if ((st = upload_csr(c, L.hR, L.R))) return st;
+      L.P.dist_rows = L.R.dist_rows = dist;
       if ((st = dvec(c, &L.invd, L.n))) return st;
       if (!L.h_invd.empty()) {
         CU(cudaMemcpyAsync(L.invd, L.h_invd.data(), (size_t)L.n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
@@ -1137,13 +1329,16 @@ static int prepare_amg(fdal_ctx *c, Amg &g) {
     if ((st = dvec(c, &L.xa, L.n))) return st;
     if ((st = dvec(c, &L.xb, L.n))) return st;
     if ((st = dvec(c, &L.b, L.n))) return st;
+    CU(cudaStreamSynchronize(c->stream));
     // host copies are no longer needed
+    const int64_t keep_nr = L.hA.nr;
     L.hA = HostCsr();
     L.hA.set = true;
-    L.hP.ci.clear(); L.hP.v.clear(); L.hP.rp.clear();
-    L.hR.ci.clear(); L.hR.v.clear(); L.hR.rp.clear();
-    L.hP.ci.shrink_to_fit(); L.hP.v.shrink_to_fit(); L.hR.ci.shrink_to_fit(); L.hR.v.shrink_to_fit();
+    L.hA.nr = keep_nr;
+    L.hP = HostCsr();
+    L.hR = HostCsr();
   }
+  if (dist && (st = dvec(c, &g.cfull, g.cn_global))) return st;
   if ((st = invert_coarse(c, g))) return st;
   g.ready = true;
   return FDAL_OK;
@@ -1207,7 +1402,7 @@ int fdal_create(fdal_ctx **out, const fdal_config *cfg) {
   }
   cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, cfg->device);
   // tuning knobs (measurement only; defaults are the shipped configuration)
-  if (const char *e = getenv("FDAL_SPMV")) c->prefer_stream = strcmp(e, "classic") != 0;
+  if (const char *e = getenv("FDAL_SPMV")) c->prefer_stream = strcmp(e, "stream") == 0;
   if (const char *e = getenv("FDAL_UNROLL")) c->spmv_unroll = atoi(e);
   if (const char *e = getenv("FDAL_STREAM_CTAS")) c->stream_ctas_per_sm = std::max(1, atoi(e));
   *out = c;
@@ -1223,6 +1418,7 @@ void fdal_destroy(fdal_ctx *c) {
     if (w->fixed_exec) cudaGraphExecDestroy(w->fixed_exec);
   }
   for (void *p : c->allocs) cudaFree(p);
+  if (c->comm) nccl_api()->CommDestroy(c->comm);
   if (c->h_scal) cudaFreeHost(c->h_scal);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -1338,9 +1534,14 @@ int fdal_finalize(fdal_ctx *c) {
   if (!need(c, FDAL_MAT_A, "A") || !need(c, FDAL_MAT_CT, "Ct")) return FDAL_ERR_STATE;
   c->n0 = c->hmat[FDAL_MAT_A].nr;
   c->m = c->hmat[FDAL_MAT_CT].nc;
-  if (c->hmat[FDAL_MAT_CT].nr != c->n0 || c->hmat[FDAL_MAT_A].nc != c->n0) {
+  if (c->hmat[FDAL_MAT_CT].nr != c->n0 || c->hmat[FDAL_MAT_A].owned_cols() != c->n0) {
     set_err(c, "A must be n x n and Ct n x m");
     return FDAL_ERR_SHAPE;
+  }
+  const bool D = c->nranks > 1;
+  if (D && is_stokes(c) && !c->hmat[FDAL_MAT_B].set) {
+    set_err(c, "a partitioned Stokes system needs an explicit B with its halo plan");
+    return FDAL_ERR_STATE;
   }
   if (k == FDAL_KIND_LAPLACE) {
     c->nblocks = 2;
@@ -1353,7 +1554,7 @@ int fdal_finalize(fdal_ctx *c) {
       return FDAL_ERR_SHAPE;
     }
     c->nblocks = 3;
-    c->n1 = c->hmat[FDAL_MAT_BT].nc;
+    c->n1 = c->hmat[FDAL_MAT_BT].owned_cols();
     c->n2 = c->m;
     if (!need(c, FDAL_MAT_MP, "Mp")) return FDAL_ERR_STATE;
     if (c->hmat[FDAL_MAT_MP].nr != c->n1) return FDAL_ERR_SHAPE;
@@ -1395,7 +1596,12 @@ int fdal_finalize(fdal_ctx *c) {
       std::vector<double>().swap(h.v);
       std::vector<int>().swap(h.rp);
     }
-  // Ct rides in the row pass of A (k_spmv2): same thread-per-row split
+  for (int id : {FDAL_MAT_A, FDAL_MAT_BT, FDAL_MAT_B, FDAL_MAT_MP}) c->dmat[id].dist_rows = D;
+  // dots: the replicated tail blocks are counted on rank 0 only
+  {
+    const int64_t tail = k == FDAL_KIND_LAPLACE ? c->n1 : is_stokes(c) ? c->n2 : c->n1 + c->n2;
+    c->n_dot_outer = c->N - ((D && c->rank != 0) ? tail : 0);
+  }
   if (c->cfg.winv_mode == FDAL_WINV_DIAG) {
     if ((st = dvec(c, &c->d_winv, c->m))) return st;
     CU(cudaMemcpyAsync(c->d_winv, c->h_winv.data(), (size_t)c->m * sizeof(double), cudaMemcpyHostToDevice, c->stream));
@@ -1411,9 +1617,15 @@ int fdal_finalize(fdal_ctx *c) {
   if ((st = dvec(c, &c->t_N0, c->N))) return st;
   if ((st = dvec(c, &c->t_N1, c->N))) return st;
   if ((st = alloc_cg(c, c->cg11, c->n0))) return st;
+  c->cg11.dist = D;
+  c->cg11.n_dot = c->n0;
   if (is_elliptic(c)) {
-    if ((st = alloc_cg(c, c->cg22, c->n1))) return st;
-    if (k == FDAL_KIND_ELLIPTIC_IDEAL && (st = alloc_cg(c, c->cgblk, c->n0 + c->n1))) return st;
+    if ((st = alloc_cg(c, c->cg22, c->n1))) return st;  // immersed block: replicated
+    if (k == FDAL_KIND_ELLIPTIC_IDEAL) {
+      if ((st = alloc_cg(c, c->cgblk, c->n0 + c->n1))) return st;
+      c->cgblk.dist = D;
+      c->cgblk.n_dot = c->n0 + ((D && c->rank != 0) ? 0 : c->n1);
+    }
   }
   // mass solves
   if (c->cfg.winv_mode != FDAL_WINV_DIAG) {
@@ -1425,6 +1637,8 @@ int fdal_finalize(fdal_ctx *c) {
   }
   if (is_stokes(c)) {
     if ((st = alloc_cg(c, c->cgmass_p, c->n1))) return st;
+    c->cgmass_p.dist = D;
+    c->cgmass_p.n_dot = c->n1;
     if (c->cfg.mp_inv_mode == FDAL_MPINV_EXACT) {
       if ((st = invdiag_of(c, c->dmat[FDAL_MAT_MP], &c->d_mp_invdiag))) return st;
       if ((st = mass_calibrate(c, c->cgmass_p, c->dmat[FDAL_MAT_MP], c->d_mp_invdiag, &c->mass_its_p))) return st;
@@ -1449,12 +1663,12 @@ int fdal_finalize(fdal_ctx *c) {
         set_err(c, "AMG hierarchy %d not set", a);
         return FDAL_ERR_STATE;
       }
-      if (c->amg[a].lev[0].hA.nr != (a == 0 ? c->n0 : c->n1)) {
+      if (c->amg[a].lev.size() > 1 && c->amg[a].lev[0].hA.nr != (a == 0 ? c->n0 : c->n1)) {
         set_err(c, "AMG hierarchy %d: fine level has %lld rows, block has %lld", a,
                 (long long)c->amg[a].lev[0].hA.nr, (long long)(a == 0 ? c->n0 : c->n1));
         return FDAL_ERR_SHAPE;
       }
-      if ((st = prepare_amg(c, c->amg[a]))) return st;
+      if ((st = prepare_amg(c, c->amg[a], a == 0 && c->nranks > 1))) return st;
     }
   }
   // outer Krylov workspace
@@ -1777,27 +1991,90 @@ int fdal_time_kernel(fdal_ctx *c, int what, int param, int warmup, int reps, int
   return FDAL_OK;
 }
 
-// ---- multi-GPU entry points: filled in by comm.cu when built with NCCL ---------------------
-#ifndef FDAL_WITH_NCCL
+// ---- multi-GPU entry points ---------------------------------------------------------------
 int fdal_nccl_unique_id(char id_out[128]) {
-  (void)id_out;
-  return FDAL_ERR_UNSUPPORTED;
+  NcclApi *n = nccl_api();
+  if (!n->ok) return FDAL_ERR_NCCL;
+  ncclUniqueId id;
+  if (n->GetUniqueId(&id) != ncclSuccess) return FDAL_ERR_NCCL;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  memcpy(id_out, &id, 128);
+  return FDAL_OK;
 }
 int fdal_comm_init(fdal_ctx *c, const char id[128], int rank, int n_ranks) {
-  (void)id;
-  (void)rank;
-  (void)n_ranks;
   CHECK_CTX(c);
-  set_err(c, "built without NCCL");
-  return FDAL_ERR_UNSUPPORTED;
+  if (rank < 0 || n_ranks < 1 || rank >= n_ranks || !id) return FDAL_ERR_INVALID;
+  if (c->finalized || !c->allocs.empty()) {
+    set_err(c, "fdal_comm_init must precede fdal_finalize");
+    return FDAL_ERR_STATE;
+  }
+  c->rank = rank;
+  c->nranks = n_ranks;
+  if (n_ranks == 1) return FDAL_OK;
+  NcclApi *n = nccl_api();
+  if (!n->ok) {
+    set_err(c, "libnccl.so.2 could not be loaded");
+    return FDAL_ERR_NCCL;
+  }
+  CU(cudaSetDevice(c->cfg.device));
+  ncclUniqueId uid;
+  memcpy(&uid, id, 128);
+  ncclResult_t r = n->CommInitRank(&c->comm, n_ranks, uid, rank);
+  if (r != ncclSuccess) {
+    set_err(c, "ncclCommInitRank failed: %s", n->GetErrorString ? n->GetErrorString(r) : "?");
+    return FDAL_ERR_NCCL;
+  }
+  return FDAL_OK;
 }
 int fdal_set_halo(fdal_ctx *c, int matrix_id, int level, int which, int64_t n_owned_cols, int64_t n_halo,
                   const int32_t *send_counts, const int32_t *send_idx, const int32_t *recv_counts) {
-  (void)matrix_id; (void)level; (void)which; (void)n_owned_cols; (void)n_halo; (void)send_counts; (void)send_idx; (void)recv_counts;
   CHECK_CTX(c);
-  set_err(c, "built without NCCL");
-  return FDAL_ERR_UNSUPPORTED;
+  if (!send_counts || !recv_counts || n_owned_cols < 0 || n_halo < 0) return FDAL_ERR_INVALID;
+  HostCsr *h = nullptr;
+  if (matrix_id >= 0 && matrix_id < FDAL_MAT_COUNT) {
+    h = &c->hmat[matrix_id];
+  } else if (matrix_id >= FDAL_MAT_AMG_A && matrix_id <= FDAL_MAT_AMG_R) {
+    if (which < 0 || which > 1 || level < 0 || level >= (int)c->amg[which].lev.size()) return FDAL_ERR_INVALID;
+    AmgLevel &L = c->amg[which].lev[level];
+    h = matrix_id == FDAL_MAT_AMG_A ? &L.hA : matrix_id == FDAL_MAT_AMG_P ? &L.hP : &L.hR;
+  }
+  if (!h || !h->set) {
+    set_err(c, "fdal_set_halo: matrix %d (level %d) was not set", matrix_id, level);
+    return FDAL_ERR_STATE;
+  }
+  if (n_owned_cols + n_halo != h->nc) {
+    set_err(c, "fdal_set_halo: %lld owned + %lld halo columns != %lld columns", (long long)n_owned_cols,
+            (long long)n_halo, (long long)h->nc);
+    return FDAL_ERR_SHAPE;
+  }
+  int64_t ns = 0, nr = 0;
+  for (int q = 0; q < c->nranks; ++q) {
+    ns += send_counts[q];
+    nr += recv_counts[q];
+  }
+  if (nr != n_halo) {
+    set_err(c, "fdal_set_halo: recv_counts sum to %lld, expected %lld", (long long)nr, (long long)n_halo);
+    return FDAL_ERR_SHAPE;
+  }
+  for (int64_t i = 0; i < ns; ++i)
+    if (send_idx[i] < 0 || send_idx[i] >= n_owned_cols) {
+      set_err(c, "fdal_set_halo: send index out of range");
+      return FDAL_ERR_SHAPE;
+    }
+  h->has_plan = true;
+  h->n_owned = n_owned_cols;
+  h->n_halo = n_halo;
+  h->send_counts.assign(send_counts, send_counts + c->nranks);
+  h->recv_counts.assign(recv_counts, recv_counts + c->nranks);
+  h->send_idx.assign(send_idx, send_idx + ns);
+  return FDAL_OK;
 }
-#endif
+int fdal_amg_set_coarse_range(fdal_ctx *c, int which, int64_t lo, int64_t hi) {
+  CHECK_CTX(c);
+  if (which < 0 || which > 1 || lo < 0 || hi < lo) return FDAL_ERR_INVALID;
+  c->amg[which].c_lo = lo;
+  c->amg[which].c_hi = hi;
+  return FDAL_OK;
+}
 
 }  // extern "C"

@@ -175,25 +175,33 @@ struct EpiCheb {
 };
 
 // ---- CSR SpMV, TPR threads per row, grid-stride over row chunks ----------------
-// row-group partial sum with U independent (value, column, x) load chains in flight
+// row-group partial sum with U independent (value, column, x) load chains in flight per
+// lane: all U value/column loads are issued back to back (predicated, no divergence),
+// then the U gathers, then the FMAs — memory-level parallelism no longer depends on the
+// row being long enough to fill an unrolled trip.
 template <int TPR, int U>
 __device__ __forceinline__ double row_partial(const CsrDev &A, const XVec &X, int k0, int k1, int lane) {
   double s = 0.0;
-  int k = k0 + lane;
   if (U > 1) {
-    for (; k + (U - 1) * TPR < k1; k += U * TPR) {
+    for (int k = k0 + lane; k < k1; k += U * TPR) {
       double vv[U];
       int cc[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        vv[u] = __ldg(A.v + k + u * TPR);
-        cc[u] = __ldg(A.ci + k + u * TPR);
+        const int kk = k + u * TPR;
+        const bool ok = kk < k1;
+        vv[u] = ok ? __ldg(A.v + kk) : 0.0;
+        cc[u] = ok ? __ldg(A.ci + kk) : -1;
       }
+      double xx[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) s += vv[u] * xload(X, cc[u]);
+      for (int u = 0; u < U; ++u) xx[u] = cc[u] >= 0 ? xload(X, cc[u]) : 0.0;
+#pragma unroll
+      for (int u = 0; u < U; ++u) s += vv[u] * xx[u];
     }
+  } else {
+    for (int k = k0 + lane; k < k1; k += TPR) s += __ldg(A.v + k) * xload(X, __ldg(A.ci + k));
   }
-  for (; k < k1; k += TPR) s += __ldg(A.v + k) * xload(X, __ldg(A.ci + k));
   return s;
 }
 
@@ -373,15 +381,34 @@ __global__ void __launch_bounds__(kBlock) k_spmv_stream(CsrDev A, StreamPlan pla
 }
 
 // ---- dense GEMV for the coarsest AMG level: y = Ainv b (one warp per row) --------
-__global__ void __launch_bounds__(kBlock) k_gemv(int n, const double *__restrict__ Ainv, const double *__restrict__ b,
-                                                  double *__restrict__ y) {
+// rows [0, nrows) of the given row-major slab (ld = ncols): multi-GPU ranks apply only
+// their rows of the replicated inverse
+__global__ void __launch_bounds__(kBlock) k_gemv(int nrows, int ncols, const double *__restrict__ Ainv,
+                                                  const double *__restrict__ b, double *__restrict__ y) {
   const int warp = (blockIdx.x * kBlock + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= n) return;
-  const double *row = Ainv + (size_t)warp * n;
+  if (warp >= nrows) return;
+  const double *row = Ainv + (size_t)warp * ncols;
   double s = 0.0;
-  for (int k = lane; k < n; k += 32) s += __ldg(row + k) * __ldg(b + k);
+  for (int k = lane; k < ncols; k += 32) s += __ldg(row + k) * __ldg(b + k);
   s = warp_sum(s);
   if (lane == 0) y[warp] = s;
+}
+// halo pack: buf[i] = x[idx[i]]
+__global__ void __launch_bounds__(kBlock) k_pack(int n, const int *__restrict__ idx, const double *__restrict__ x,
+                                                  double *__restrict__ buf) {
+  for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) buf[i] = x[idx[i]];
+}
+// the EpiCouple epilogue as a stand-alone pass (multi-GPU: after the all-reduce of C x)
+__global__ void __launch_bounds__(kBlock) k_couple_elem(int n, const double *__restrict__ w,
+                                                         const double *__restrict__ winv, double a,
+                                                         const double *__restrict__ add, double *y1, double *t) {
+  for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+    const double s = w[i];
+    if (y1) y1[i] = s;
+    double tv = a * (winv ? winv[i] * s : s);
+    if (add) tv += add[i];
+    t[i] = tv;
+  }
 }
 
 // ---- Krylov vector kernels (K9-K11) ------------------------------------------------

@@ -1,0 +1,283 @@
+"""Row partition of the AL solve path over the GPUs of one box (host, setup only).
+
+The reference is serial; this decomposition is new.  Rows of the
+background unknowns (and, for Stokes, of the pressure unknowns) are split into
+contiguous ranges after a locality-preserving renumbering; every matrix with those
+rows is split the same way; the multiplier block (m <= ~10^5) and the immersed blocks
+are replicated on every rank.  A row-partitioned matrix numbers its columns
+``[owned | halo]`` and carries a halo plan (who sends which owned entries to whom);
+the CUDA library packs, exchanges (NCCL send/recv) and gathers through that plan.
+
+  SpMV(A, Bt, B, Mp, AMG A_l/P_l/R_l) : halo exchange of the column space, local rows
+  C x                                  : local partial over owned columns + all-reduce(m)
+  Ct t                                 : purely local (t replicated)
+  Krylov dots                          : local partial + all-reduce; replicated tail
+                                         blocks are counted on rank 0 only
+  coarsest AMG level                   : right-hand side all-reduced into a replicated
+                                         vector, every rank applies its rows of the inverse
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import _binding as b
+
+
+def split_offsets(n: int, nranks: int, align: int = 1) -> np.ndarray:
+    """Contiguous, nearly equal ranges; boundaries are multiples of `align`
+    (keeps the components of one node on one rank)."""
+    units = n // align
+    base, rem = divmod(units, nranks)
+    counts = np.array([base + (1 if r < rem else 0) for r in range(nranks)], dtype=np.int64) * align
+    counts[-1] += n - counts.sum()
+    return np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+
+
+@dataclass
+class HaloPlan:
+    n_owned: int
+    n_halo: int
+    send_counts: np.ndarray  # int32[nranks]
+    send_idx: np.ndarray  # int32[sum(send_counts)], local owned indices, grouped by destination rank
+    recv_counts: np.ndarray  # int32[nranks]; halo entries are ordered by owner rank, then global index
+    halo_globals: np.ndarray  # global (renumbered) column of each halo entry (for tests)
+
+
+@dataclass
+class DistCsr:
+    local: sp.csr_matrix  # rows: owned rows; columns: [owned | halo]
+    plan: HaloPlan | None  # None: column space is replicated / fully local
+
+
+def localize(A: sp.csr_matrix, row_off: np.ndarray, col_off: np.ndarray, rank: int) -> DistCsr:
+    """Rows row_off[rank]:row_off[rank+1] of the (renumbered) global matrix with a halo plan
+    over the column space partitioned by col_off."""
+    nranks = len(row_off) - 1
+    A = A.tocsr()
+    c0, c1 = int(col_off[rank]), int(col_off[rank + 1])
+    sub = A[int(row_off[rank]): int(row_off[rank + 1])].tocsr()
+    cols = sub.indices.astype(np.int64)
+    owned = (cols >= c0) & (cols < c1)
+    halo_globals = np.unique(cols[~owned])
+    newcol = np.empty_like(cols)
+    newcol[owned] = cols[owned] - c0
+    newcol[~owned] = (c1 - c0) + np.searchsorted(halo_globals, cols[~owned])
+    local = sp.csr_matrix((sub.data, newcol.astype(np.int32), sub.indptr), shape=(sub.shape[0], (c1 - c0) + halo_globals.size))
+    owner = np.searchsorted(col_off, halo_globals, side="right") - 1
+    recv_counts = np.bincount(owner, minlength=nranks).astype(np.int32)
+    # what every other rank needs from my owned range
+    send_lists = []
+    for q in range(nranks):
+        if q == rank:
+            send_lists.append(np.empty(0, dtype=np.int64))
+            continue
+        subq = A[int(row_off[q]): int(row_off[q + 1])]
+        cq = np.unique(subq.indices)
+        mine = cq[(cq >= c0) & (cq < c1)]
+        send_lists.append(mine - c0)
+    send_counts = np.array([s.size for s in send_lists], dtype=np.int32)
+    send_idx = np.concatenate(send_lists).astype(np.int32) if send_lists else np.empty(0, np.int32)
+    plan = HaloPlan(c1 - c0, int(halo_globals.size), send_counts, send_idx, recv_counts, halo_globals)
+    return DistCsr(local, plan)
+
+
+def block0_order(prob) -> tuple[np.ndarray, int]:
+    """new->old order of the background block and the node block size.  Vector-valued
+    blocks numbered component-wise ([u_x|u_y|u_z], DoFRenumbering::component_wise) are
+    interleaved node-major so that a contiguous range is a spatial slab holding all
+    components of its nodes."""
+    n = prob.A.shape[0]
+    comp = prob.amg_comp.get(b.AMG_A11)
+    if comp is None:
+        return np.arange(n, dtype=np.int64), 1
+    dim = int(comp.max()) + 1
+    ns = n // dim
+    node = np.arange(ns, dtype=np.int64)
+    order = (node[:, None] + ns * np.arange(dim, dtype=np.int64)[None, :]).reshape(-1)
+    return order, dim
+
+
+def coarse_order(P: sp.csr_matrix, fine_off: np.ndarray):
+    """Ownership of the coarse unknowns: a coarse unknown lives where the fine row with the
+    largest weight in its column of P lives.  Returns new->old order and the offsets."""
+    nranks = len(fine_off) - 1
+    Pc = P.tocsc()
+    nc = Pc.shape[1]
+    owner = np.zeros(nc, dtype=np.int64)
+    absd = np.abs(Pc.data)
+    # arg-max per column via a stable sort on (column, -|value|)
+    col_of = np.repeat(np.arange(nc), np.diff(Pc.indptr))
+    key = np.lexsort((-absd, col_of))
+    first = Pc.indptr[:-1]
+    has = np.diff(Pc.indptr) > 0
+    rows_max = np.zeros(nc, dtype=np.int64)
+    rows_max[has] = Pc.indices[key[first[has]]]
+    owner = np.searchsorted(fine_off, rows_max, side="right") - 1
+    owner[~has] = 0
+    order = np.lexsort((np.arange(nc), owner)).astype(np.int64)
+    counts = np.bincount(owner, minlength=nranks)
+    off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    return order, off
+
+
+@dataclass
+class LocalLevel:
+    A: DistCsr
+    P: DistCsr | None
+    R: DistCsr | None
+    inv_diag: np.ndarray | None
+    lambda_max: float
+
+
+@dataclass
+class LocalHierarchy:
+    levels: list
+    coarse_A: sp.csr_matrix  # replicated (renumbered) coarsest operator
+    coarse_off: np.ndarray
+    cheb_degree: int
+    eig_ratio: float
+    replicated: bool = False
+
+
+@dataclass
+class LocalProblem:
+    rank: int
+    nranks: int
+    config: object
+    mats: dict = field(default_factory=dict)  # matrix id -> DistCsr
+    amg: dict = field(default_factory=dict)  # which -> LocalHierarchy
+    winv_diag: np.ndarray | None = None
+    off0: np.ndarray | None = None
+    off1: np.ndarray | None = None
+    order0: np.ndarray | None = None
+    order1: np.ndarray | None = None
+    sizes_global: tuple = ()
+    sizes_local: tuple = ()
+
+    # ---- vectors ---------------------------------------------------------------------
+    def scatter(self, x_global: np.ndarray) -> np.ndarray:
+        """Global block vector -> this rank's local vector [block0_loc | block1_loc/rep | rep]."""
+        n0 = self.sizes_global[0]
+        parts = [x_global[:n0][self.order0][self.off0[self.rank]: self.off0[self.rank + 1]]]
+        rest = x_global[n0:]
+        if self.off1 is not None:
+            n1 = self.sizes_global[1]
+            parts.append(rest[:n1][self.order1][self.off1[self.rank]: self.off1[self.rank + 1]])
+            parts.append(rest[n1:])
+        else:
+            parts.append(rest)
+        return np.concatenate(parts)
+
+    def gather(self, locals_: list) -> np.ndarray:
+        """Inverse of scatter given the local vectors of all ranks (tests / output)."""
+        n0 = self.sizes_global[0]
+        out = np.zeros(sum(self.sizes_global))
+        b0 = np.concatenate([v[: self.off0[r + 1] - self.off0[r]] for r, v in enumerate(locals_)])
+        out[:n0][self.order0] = b0
+        if self.off1 is not None:
+            n1 = self.sizes_global[1]
+            b1 = np.concatenate([
+                v[self.off0[r + 1] - self.off0[r]: self.off0[r + 1] - self.off0[r] + self.off1[r + 1] - self.off1[r]]
+                for r, v in enumerate(locals_)])
+            tmp = np.zeros(n1)
+            tmp[self.order1] = b1
+            out[n0:n0 + n1] = tmp
+            out[n0 + n1:] = locals_[0][(self.off0[1] - self.off0[0]) + (self.off1[1] - self.off1[0]):]
+        else:
+            out[n0:] = locals_[0][self.off0[1] - self.off0[0]:]
+        return out
+
+
+def _perm(A, row_order, col_order):
+    A = A.tocsr()
+    if row_order is not None:
+        A = A[row_order]
+    if col_order is not None:
+        A = A[:, col_order]
+    A = A.tocsr()
+    A.sort_indices()
+    return A
+
+
+def distribute_hierarchy(H, order0, off0, rank, nranks) -> LocalHierarchy:
+    levels = []
+    order_f, off_f = order0, off0
+    nl = len(H.levels)
+    Aperm = _perm(H.levels[0].A, order_f, order_f)
+    for l in range(nl - 1):
+        L = H.levels[l]
+        order_c, off_c = coarse_order(_perm(L.P, order_f, None), off_f)
+        Pp = _perm(L.P, order_f, order_c)
+        Rp = _perm(L.R if L.R is not None else L.P.T, order_c, order_f)
+        levels.append(LocalLevel(
+            A=localize(Aperm, off_f, off_f, rank),
+            P=localize(Pp, off_f, off_c, rank),
+            R=localize(Rp, off_c, off_f, rank),
+            inv_diag=None if L.inv_diag is None else L.inv_diag[order_f][off_f[rank]: off_f[rank + 1]],
+            lambda_max=L.lambda_max,
+        ))
+        order_f, off_f = order_c, off_c
+        Aperm = _perm(H.levels[l + 1].A, order_f, order_f)
+    return LocalHierarchy(levels=levels, coarse_A=Aperm, coarse_off=off_f, cheb_degree=H.cheb_degree,
+                          eig_ratio=H.eig_ratio)
+
+
+def distribute_problem(prob, hierarchies: dict, rank: int, nranks: int) -> LocalProblem:
+    """This rank's share of a Problem (+ AMG hierarchies)."""
+    kind = prob.config.kind
+    n, m = prob.Ct.shape
+    order0, bs = block0_order(prob)
+    off0 = split_offsets(n, nranks, bs)
+    lp = LocalProblem(rank=rank, nranks=nranks, config=prob.config, order0=order0, off0=off0,
+                      sizes_global=prob.sizes, winv_diag=prob.winv_diag)
+    rep_off = np.array([0] + [m] * nranks, dtype=np.int64)  # unused: replicated spaces have no plan
+    A = _perm(prob.A, order0, order0)
+    lp.mats[b.MAT_A] = localize(A, off0, off0, rank)
+    Ct = _perm(prob.Ct, order0, None)
+    lp.mats[b.MAT_CT] = DistCsr(Ct[off0[rank]: off0[rank + 1]].tocsr(), None)
+    C = sp.csr_matrix(Ct.T)
+    lp.mats[b.MAT_C] = DistCsr(C[:, off0[rank]: off0[rank + 1]].tocsr(), None)
+    lp.mats[b.MAT_M] = DistCsr(prob.M.tocsr(), None)
+    n_loc = int(off0[rank + 1] - off0[rank])
+    if kind in (b.KIND_STOKES, b.KIND_STOKES_DIAG_MINRES):
+        n_p = prob.Bt.shape[1]
+        order1 = np.arange(n_p, dtype=np.int64)
+        off1 = split_offsets(n_p, nranks)
+        lp.order1, lp.off1 = order1, off1
+        Bt = _perm(prob.Bt, order0, order1)
+        lp.mats[b.MAT_BT] = localize(Bt, off0, off1, rank)
+        lp.mats[b.MAT_B] = localize(sp.csr_matrix(Bt.T), off1, off0, rank)
+        lp.mats[b.MAT_MP] = localize(_perm(prob.Mp, order1, order1), off1, off1, rank)
+        lp.sizes_local = (n_loc, int(off1[rank + 1] - off1[rank]), m)
+    elif kind == b.KIND_LAPLACE:
+        lp.sizes_local = (n_loc, m)
+    else:
+        lp.mats[b.MAT_A2] = DistCsr(prob.A2.tocsr(), None)
+        lp.sizes_local = (n_loc, m, m)
+    for which, H in hierarchies.items():
+        if which == b.AMG_A11:
+            lp.amg[which] = distribute_hierarchy(H, order0, off0, rank, nranks)
+        else:  # immersed block: replicated hierarchy
+            lp.amg[which] = H
+    return lp
+
+
+def setup_local_context(ctx, lp: LocalProblem, uid: bytes):
+    """Hand this rank's LocalProblem to its ALContext (after ``comm_init``) and finalize."""
+    ctx.comm_init(uid, lp.rank, lp.nranks)
+    for mid, dc in lp.mats.items():
+        ctx.set_csr(mid, dc.local)
+        if dc.plan is not None:
+            ctx.set_halo(mid, dc.plan)
+    if lp.winv_diag is not None:
+        ctx.set_diag(b.DIAG_W_INV, lp.winv_diag)
+    for which, H in lp.amg.items():
+        if isinstance(H, LocalHierarchy):
+            ctx.set_amg_local(which, H)
+        else:
+            ctx.set_amg(which, H)
+    ctx.finalize()
+    return ctx

@@ -91,7 +91,11 @@ enum {
   FDAL_MAT_C = 5,   /* optional explicit C (m x n), else transposed Ct        */
   FDAL_MAT_M = 6,   /* immersed mass matrix (m x m)                           */
   FDAL_MAT_MP = 7,  /* Stokes pressure mass matrix (n_p x n_p)                */
-  FDAL_MAT_COUNT = 8
+  FDAL_MAT_COUNT = 8,
+  /* only for fdal_set_halo: the matrices of one AMG level (which, level) */
+  FDAL_MAT_AMG_A = 100,
+  FDAL_MAT_AMG_P = 101,
+  FDAL_MAT_AMG_R = 102
 };
 
 /* ---- W^-1 (augmented_lagrangian_preconditioner.h `invW`) --------------- */
@@ -267,15 +271,25 @@ int fdal_time_kernel(fdal_ctx *ctx, int what, int param, int warmup, int reps,
 
 /* ---- multi-GPU (one process per GPU) -------------------------------------
  * No reference counterpart (the reference is serial).  Rows of the
- * background unknowns are partitioned; the multiplier block is replicated. */
+ * background (and pressure) unknowns are partitioned into contiguous ranges; the
+ * multiplier block and the immersed blocks are replicated.  Call order:
+ * fdal_create, fdal_comm_init, fdal_set_csr / fdal_amg_set_level with the LOCAL rows
+ * (columns numbered [owned | halo]), fdal_set_halo for every matrix that has a halo,
+ * fdal_amg_set_coarse with the full (replicated) coarsest operator +
+ * fdal_amg_set_coarse_range, fdal_finalize.  Vectors passed to the apply / solve
+ * entry points are then the rank-local [block0_loc | block1_loc | replicated tail]. */
 int fdal_nccl_unique_id(char id_out[128]);
 int fdal_comm_init(fdal_ctx *ctx, const char id[128], int rank, int n_ranks);
 /* halo plan of a row-partitioned matrix whose columns are numbered
- * [owned | halo]: for each peer the owned entries to send and the number of
- * halo entries received (halo entries are ordered by peer rank). */
+ * [owned | halo]: for each peer the owned entries to send (send_idx, grouped by
+ * destination rank) and the number of halo entries received (halo entries are
+ * ordered by owner rank).  matrix_id: FDAL_MAT_* or FDAL_MAT_AMG_{A,P,R} with
+ * (which, level). */
 int fdal_set_halo(fdal_ctx *ctx, int matrix_id, int level, int which,
                   int64_t n_owned_cols, int64_t n_halo, const int32_t *send_counts,
                   const int32_t *send_idx, const int32_t *recv_counts);
+/* rows [lo, hi) of the replicated coarsest operator belong to this rank */
+int fdal_amg_set_coarse_range(fdal_ctx *ctx, int which, int64_t lo, int64_t hi);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,180 @@
+"""Host-side logic of the multi-GPU path (row partition, halo plans, replicated blocks),
+exercised with world_size-2 `gloo` process groups on CPU: every rank builds its local
+matrices with partition.py, halo values travel through torch.distributed exactly as the
+plan prescribes, and the assembled results must equal the serial products."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from fictitious_domain_al_preconditioners_b200 import _binding as b
+from fictitious_domain_al_preconditioners_b200 import partition as part
+from fictitious_domain_al_preconditioners_b200 import synthetic as syn
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def halo_exchange(dc: part.DistCsr, x_owned: np.ndarray, rank: int, nranks: int) -> np.ndarray:
+    """[owned | halo] vector of a DistCsr, halo filled through the plan (gloo)."""
+    plan = dc.plan
+    if plan is None:
+        return x_owned
+    soff = np.concatenate([[0], np.cumsum(plan.send_counts)])
+    out = [x_owned[plan.send_idx[soff[q]: soff[q + 1]]] for q in range(nranks)]
+    gathered = [None] * nranks
+    dist.all_gather_object(gathered, out)
+    halo = np.concatenate([gathered[q][rank] for q in range(nranks)]) if plan.n_halo else np.empty(0)
+    assert halo.size == plan.n_halo
+    for q in range(nranks):
+        assert gathered[q][rank].size == plan.recv_counts[q]
+    return np.concatenate([x_owned, halo])
+
+
+def dist_spmv(dc, x_owned, rank, nranks):
+    return dc.local @ halo_exchange(dc, x_owned, rank, nranks)
+
+
+def allreduce(v):
+    t = torch.from_numpy(np.ascontiguousarray(v, dtype=np.float64).copy())
+    dist.all_reduce(t)
+    return t.numpy()
+
+
+def dist_vcycle(LH, bvec, rank, nranks, l=0):
+    """Distributed restatement of the V-cycle on LocalHierarchy pieces."""
+    if l == len(LH.levels):
+        off = LH.coarse_off
+        full = np.zeros(LH.coarse_A.shape[0])
+        full[off[rank]: off[rank + 1]] = bvec
+        full = allreduce(full)
+        return np.linalg.solve(LH.coarse_A.toarray(), full)[off[rank]: off[rank + 1]]
+    L = LH.levels[l]
+    invd = L.inv_diag
+    beta, alpha = 1.1 * L.lambda_max, L.lambda_max / LH.eig_ratio
+    delta, theta = 0.5 * (beta - alpha), 0.5 * (beta + alpha)
+    s1 = theta / delta
+    mv = lambda v: dist_spmv(L.A, v, rank, nranks)  # noqa: E731
+
+    def cheb(x, zero):
+        rho = 1.0 / s1
+        d = invd * (bvec if zero else bvec - mv(x)) / theta
+        x = d.copy() if zero else x + d
+        for _ in range(1, LH.cheb_degree):
+            rho1 = 1.0 / (2 * s1 - rho)
+            d = rho1 * rho * d + 2 * rho1 / delta * invd * (bvec - mv(x))
+            x = x + d
+            rho = rho1
+        return x
+
+    x = cheb(None, True)
+    r = bvec - mv(x)
+    e = dist_vcycle(LH, dist_spmv(L.R, r, rank, nranks), rank, nranks, l + 1)
+    x = x + dist_spmv(L.P, e, rank, nranks)
+    return cheb(x, False)
+
+
+def _worker(rank, nranks, port, case, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=nranks)
+    try:
+        from tests.test_oracle_known_answers import vcycle_ref
+
+        if case == "stokes":
+            prob = syn.stokes_immersed_boundary(dim=2, nel=8, diagonal_mass=True)
+        else:
+            prob = syn.immersed_laplace(r_bg=4)
+        H = syn.build_hierarchies(prob, max_coarse=40)
+        lp = part.distribute_problem(prob, H, rank, nranks)
+        rng = np.random.default_rng(3)
+        X = rng.uniform(-1, 1, prob.n_dofs)
+        xl = lp.scatter(X)
+        n, m = prob.Ct.shape
+        n0l = lp.sizes_local[0]
+        x0 = xl[:n0l]
+        res = {}
+        # A x0 (halo), Ct lam (local), C x0 (all-reduce)
+        lam = X[-m:]
+        y0 = dist_spmv(lp.mats[b.MAT_A], x0, rank, nranks) + lp.mats[b.MAT_CT].local @ lam
+        cx = allreduce(lp.mats[b.MAT_C].local @ x0)
+        ref0 = (prob.A @ X[:n] + prob.Ct @ lam)[lp.order0][lp.off0[rank]: lp.off0[rank + 1]]
+        res["A"] = float(np.abs(y0 - ref0).max())
+        res["C"] = float(np.abs(cx - prob.Ct.T @ X[:n]).max())
+        if case == "stokes":
+            n1l = lp.sizes_local[1]
+            n_p = prob.Bt.shape[1]
+            x1 = xl[n0l: n0l + n1l]
+            yb = dist_spmv(lp.mats[b.MAT_BT], x1, rank, nranks)
+            refb = (prob.Bt @ X[n: n + n_p])[lp.order0][lp.off0[rank]: lp.off0[rank + 1]]
+            res["Bt"] = float(np.abs(yb - refb).max())
+            yB = dist_spmv(lp.mats[b.MAT_B], x0, rank, nranks)
+            res["B"] = float(np.abs(yB - (prob.Bt.T @ X[:n])[lp.off1[rank]: lp.off1[rank + 1]]).max())
+            ym = dist_spmv(lp.mats[b.MAT_MP], x1, rank, nranks)
+            res["Mp"] = float(np.abs(ym - (prob.Mp @ X[n: n + n_p])[lp.off1[rank]: lp.off1[rank + 1]]).max())
+        # Krylov dot with the replicated tail counted once
+        n_dot = xl.size - (0 if rank == 0 else m)
+        res["dot"] = float(abs(allreduce(np.array([xl[:n_dot] @ xl[:n_dot]]))[0] - X @ X))
+        # scatter / gather round trip
+        allx = [None] * nranks
+        dist.all_gather_object(allx, xl)
+        res["roundtrip"] = float(np.abs(lp.gather(allx) - X).max())
+        # distributed V-cycle == serial V-cycle
+        LH = lp.amg[b.AMG_A11]
+        z = dist_vcycle(LH, x0, rank, nranks)
+        zref = vcycle_ref(H[b.AMG_A11], X[:n])[lp.order0][lp.off0[rank]: lp.off0[rank + 1]]
+        res["vcycle"] = float(np.abs(z - zref).max() / np.abs(zref).max())
+        res["levels"] = len(LH.levels)
+        q.put((rank, res))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case", ["laplace", "stokes"])
+def test_two_rank_partition_matches_serial(case):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, case, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, res in out:
+        assert res.pop("levels") >= 1
+        for k, v in res.items():
+            assert v < 1e-11, (rank, k, v)
+
+
+def test_split_offsets_keeps_nodes_together():
+    off = part.split_offsets(2 * 17 * 17, 3, align=2)
+    assert off[0] == 0 and off[-1] == 2 * 17 * 17
+    assert all(o % 2 == 0 for o in off)
+    assert np.all(np.diff(off) > 0)
+
+
+def test_halo_plan_is_consistent_single_process():
+    """send lists of rank q towards r hold exactly the halo columns r expects from q."""
+    prob = syn.immersed_laplace(r_bg=4)
+    n = prob.A.shape[0]
+    P = 4
+    off = part.split_offsets(n, P)
+    dcs = [part.localize(prob.A, off, off, r) for r in range(P)]
+    for r in range(P):
+        roff = np.concatenate([[0], np.cumsum(dcs[r].plan.recv_counts)])
+        for q in range(P):
+            soff = np.concatenate([[0], np.cumsum(dcs[q].plan.send_counts)])
+            sent = dcs[q].plan.send_idx[soff[r]: soff[r + 1]] + off[q]
+            want = dcs[r].plan.halo_globals[roff[q]: roff[q + 1]]
+            assert np.array_equal(sent, want)
