@@ -46,7 +46,9 @@ def build_problem(w):
     from fictitious_domain_al_preconditioners_b200 import synthetic as syn
 
     if w["kind"] == "stokes":
-        prob = syn.stokes_immersed_boundary(dim=w["dim"], nel=w["nel"], diagonal_mass=w["diagonal_mass"])
+        # node-major numbering: the velocity block and the finest AMG operator go to BSR
+        prob = syn.stokes_immersed_boundary(dim=w["dim"], nel=w["nel"], diagonal_mass=w["diagonal_mass"],
+                                            numbering="node")
     else:
         prob = syn.immersed_laplace(r_bg=w["r_bg"], diagonal_inverse=True)
     H = syn.build_hierarchies(prob)
@@ -214,25 +216,24 @@ def run_ours(args, w, wname):
     prob.config.device = local_rank
     prob.config.use_graphs = not args.no_graphs
     t0 = time.perf_counter()
+    from fictitious_domain_al_preconditioners_b200 import partition as part
+
+    lp = part.distribute_problem(prob, H, rank, world)
+    if not args.no_bsr:
+        prob.config.block_size = lp.block_size
+    ctx = ALContext(prob.config)
+    uid = [bytes(128)]
     if world > 1:
         import torch.distributed as dist
 
-        from fictitious_domain_al_preconditioners_b200 import partition as part
-
         gloo = dist.new_group(backend="gloo")
-        lp = part.distribute_problem(prob, H, rank, world)
-        ctx = ALContext(prob.config)
         uid = [ctx.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0, group=gloo)
-        part.setup_local_context(ctx, lp, uid[0])
-        rhs = lp.scatter(prob.rhs)
-        if prob.augment_rhs:
-            rhs = ctx.augment_rhs(rhs)
-        N = rhs.size
-    else:
-        ctx = syn.setup_context(ALContext(prob.config), prob, H)
-        rhs = ctx.augment_rhs(prob.rhs) if prob.augment_rhs else prob.rhs.copy()
-        N = prob.n_dofs
+    part.setup_local_context(ctx, lp, uid[0])
+    rhs = lp.scatter(prob.rhs)
+    if prob.augment_rhs:
+        rhs = ctx.augment_rhs(rhs)
+    N = rhs.size
     t_setup = time.perf_counter() - t0
 
     def barrier():
@@ -326,7 +327,8 @@ def run_ours(args, w, wname):
                        "outer_iterations": int(last.outer_iterations), "inner_iterations": int(last.inner_iterations),
                        "mass_iterations": int(last.mass_iterations), "final_residual": last.final_residual,
                        "setup_s": {"generate+amg_host": t_gen, "upload+finalize": t_setup},
-                       "wall_ms_per_step": wall / args.steps * 1e3, "graphs": bool(prob.config.use_graphs)},
+                       "wall_ms_per_step": wall / args.steps * 1e3, "graphs": bool(prob.config.use_graphs),
+                       "block_size": int(prob.config.block_size)},
             "e2e": {"value": total_dofs / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 16 * N, "d2h_bytes_per_step": 8 * N,
                     "ms_per_step": e2e_s * 1e3},
             "gpu_launches": int(sum(i.kernel_launches for i in infos)),
@@ -360,6 +362,7 @@ def main():
     ap.add_argument("--nel", type=int, default=0, help="override the refinement of the workload")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-graphs", action="store_true")
+    ap.add_argument("--no-bsr", action="store_true")
     ap.add_argument("--expected-outer", type=int, default=0)
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])

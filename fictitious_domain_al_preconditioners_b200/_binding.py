@@ -53,6 +53,8 @@ class Config(C.Structure):
         ("device", c_int32),
         ("use_graphs", c_int32),
         ("exact_mass_max_its", c_int32),
+        ("block_size", c_int32),
+        ("reserved0", c_int32),
         ("outer", Control),
         ("inner", Control),
         ("mass", Control),

@@ -33,7 +33,8 @@ def build_host_lib(force=False):
     src = os.path.join(_HERE, "csrc", "host_setup.c")
     if force or not os.path.exists(_HOST_LIB) or os.path.getmtime(_HOST_LIB) < os.path.getmtime(src):
         subprocess.run(
-            ["/usr/bin/gcc", "-O2", "-fPIC", "-shared", "-o", _HOST_LIB, src], check=True, capture_output=True
+            ["/usr/bin/gcc", "-O3", "-fopenmp", "-fPIC", "-shared", "-o", _HOST_LIB, src], check=True,
+            capture_output=True
         )
     return _HOST_LIB
 
@@ -50,7 +51,62 @@ def _host():
             C.POINTER(C.c_int32),
             C.POINTER(C.c_int32),
         ]
+        p64, p32, pd = C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_double)
+        _lib.fdal_host_spgemm_symbolic.restype = C.c_int64
+        _lib.fdal_host_spgemm_symbolic.argtypes = [C.c_int64, C.c_int64, p64, p32, p64, p32, p64]
+        _lib.fdal_host_spgemm_numeric.restype = None
+        _lib.fdal_host_spgemm_numeric.argtypes = [C.c_int64, C.c_int64, p64, p32, pd, p64, p32, pd, p64, p32, pd]
     return _lib
+
+
+_GPU_SPGEMM_MIN_NNZ = 20_000_000
+
+
+import sys
+import time
+
+_VERBOSE = bool(os.environ.get("FDAL_VERBOSE_SETUP"))
+
+
+def _log(msg):
+    if _VERBOSE:
+        sys.stderr.write(f"[setup] {msg}\n")
+        sys.stderr.flush()
+
+
+def _spgemm(A: sp.csr_matrix, B: sp.csr_matrix) -> sp.csr_matrix:
+    """C = A @ B (setup phase).  Large products use the OpenMP Gustavson kernel in
+    csrc/host_setup.c (scipy's csr_matmat is single-threaded: minutes on the 10^8..10^9
+    non-zero fine levels); small ones scipy.  cuSPARSE SpGEMM through torch was tried and
+    dropped: it runs out of workspace ("insufficient resources") beyond ~3e7 non-zeros."""
+    t0 = time.perf_counter()
+    if A.nnz >= 2_000_000:
+        A = A.tocsr()
+        B = B.tocsr()
+        p64, p32, pd = C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_double)
+        Ap = np.ascontiguousarray(A.indptr, dtype=np.int64)
+        Aj = np.ascontiguousarray(A.indices, dtype=np.int32)
+        Ax = np.ascontiguousarray(A.data, dtype=np.float64)
+        Bp = np.ascontiguousarray(B.indptr, dtype=np.int64)
+        Bj = np.ascontiguousarray(B.indices, dtype=np.int32)
+        Bx = np.ascontiguousarray(B.data, dtype=np.float64)
+        Cp = np.empty(A.shape[0] + 1, dtype=np.int64)
+        lib = _host()
+        nnz = lib.fdal_host_spgemm_symbolic(A.shape[0], B.shape[1], Ap.ctypes.data_as(p64), Aj.ctypes.data_as(p32),
+                                            Bp.ctypes.data_as(p64), Bj.ctypes.data_as(p32), Cp.ctypes.data_as(p64))
+        Cj = np.empty(max(nnz, 1), dtype=np.int32)
+        Cx = np.empty(max(nnz, 1), dtype=np.float64)
+        lib.fdal_host_spgemm_numeric(A.shape[0], B.shape[1], Ap.ctypes.data_as(p64), Aj.ctypes.data_as(p32),
+                                     Ax.ctypes.data_as(pd), Bp.ctypes.data_as(p64), Bj.ctypes.data_as(p32),
+                                     Bx.ctypes.data_as(pd), Cp.ctypes.data_as(p64), Cj.ctypes.data_as(p32),
+                                     Cx.ctypes.data_as(pd))
+        C_ = sp.csr_matrix((Cx[:nnz], Cj[:nnz], Cp), shape=(A.shape[0], B.shape[1]))
+        C_.has_sorted_indices = True
+        _log(f"spgemm(omp) {A.shape}x{B.shape} nnz {A.nnz}x{B.nnz}->{C_.nnz}: {time.perf_counter()-t0:.2f}s")
+        return C_
+    C_ = (A @ B).tocsr()
+    _log(f"spgemm(cpu) {A.shape}x{B.shape} nnz {A.nnz}x{B.nnz}->{C_.nnz}: {time.perf_counter()-t0:.2f}s")
+    return C_
 
 
 @dataclass
@@ -90,6 +146,51 @@ def _strength_graph(A: sp.csr_matrix, theta: float, comp: np.ndarray | None):
     return S
 
 
+def _cuda_ok(nnz: int) -> bool:
+    if nnz < _GPU_SPGEMM_MIN_NNZ:
+        return False
+    try:
+        import torch
+
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def _to_torch_csr(M: sp.csr_matrix):
+    import torch
+
+    M = M.tocsr()
+    return torch.sparse_csr_tensor(
+        torch.from_numpy(M.indptr.astype(np.int64)).cuda(), torch.from_numpy(M.indices.astype(np.int64)).cuda(),
+        torch.from_numpy(M.data.astype(np.float64)).cuda(), size=M.shape)
+
+
+def _strength_graph_gpu(A: sp.csr_matrix, theta: float, comp: np.ndarray | None):
+    """Same criterion as _strength_graph, evaluated on the GPU for the 10^8..10^9 non-zero
+    fine levels (A is symmetric, so the selected pattern already is)."""
+    import torch
+
+    n = A.shape[0]
+    crow = torch.from_numpy(A.indptr.astype(np.int64)).cuda()
+    col = torch.from_numpy(A.indices.astype(np.int64)).cuda()
+    val = torch.from_numpy(A.data).cuda()
+    row = torch.repeat_interleave(torch.arange(n, device="cuda"), crow[1:] - crow[:-1])
+    d = torch.from_numpy(np.abs(A.diagonal())).cuda()
+    keep = (row != col) & (val.abs() >= theta * torch.sqrt(d[row] * d[col])) & (val != 0)
+    if comp is not None:
+        cc = torch.from_numpy(comp.astype(np.int64)).cuda()
+        keep &= cc[row] == cc[col]
+    rk, ck = row[keep], col[keep]
+    cnt = torch.bincount(rk, minlength=n)
+    indptr = np.zeros(n + 1, dtype=np.int64)
+    indptr[1:] = torch.cumsum(cnt, 0).cpu().numpy()
+    S = sp.csr_matrix((np.ones(int(indptr[-1]), dtype=np.int8), ck.to(torch.int32).cpu().numpy(), indptr), shape=(n, n))
+    del row, col, val, keep, rk, ck
+    torch.cuda.empty_cache()
+    return S
+
+
 def aggregate(S: sp.csr_matrix) -> tuple[np.ndarray, int]:
     n = S.shape[0]
     indptr = np.ascontiguousarray(S.indptr, dtype=np.int64)
@@ -111,7 +212,19 @@ def estimate_lambda_max(A: sp.csr_matrix, inv_diag: np.ndarray, iters: int = 20)
     if n <= 3:
         M = (sp.diags(s) @ A @ sp.diags(s)).toarray()
         return float(np.max(np.linalg.eigvalsh(0.5 * (M + M.T))))
-    op = spla.LinearOperator((n, n), matvec=lambda x: s * (A @ (s * x)), dtype=np.float64)
+    if _cuda_ok(A.nnz):
+        import torch
+
+        At = _to_torch_csr(A)
+        st = torch.from_numpy(s).cuda()
+
+        def mv(x):
+            xt = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64).ravel()).cuda()
+            return (st * (At @ (st * xt))).cpu().numpy()
+    else:
+        def mv(x):
+            return s * (A @ (s * x))
+    op = spla.LinearOperator((n, n), matvec=mv, dtype=np.float64)
     v0 = 1.0 + 0.5 * np.sin(np.arange(n) * 0.7853981633974483 + 0.3)
     try:
         lam = spla.eigsh(op, k=1, which="LA", v0=v0, ncv=min(n - 1, max(iters, 4)), maxiter=50, tol=1e-3,
@@ -153,26 +266,32 @@ def build_hierarchy(
     H = Hierarchy(cheb_degree=cheb_degree, eig_ratio=eig_ratio)
     while True:
         n = A.shape[0]
+        t0 = time.perf_counter()
         diag = A.diagonal()
         inv_diag = 1.0 / diag
         lam = estimate_lambda_max(A, inv_diag)
+        _log(f"level {len(H.levels)}: n={n} nnz={A.nnz} lambda_max {time.perf_counter()-t0:.2f}s")
         L = Level(A=A, inv_diag=inv_diag, lambda_max=lam)
         H.levels.append(L)
         if n <= max_coarse or len(H.levels) >= max_levels:
             break
-        S = _strength_graph(A, theta, comp)
+        t0 = time.perf_counter()
+        S = _strength_graph_gpu(A, theta, comp) if _cuda_ok(A.nnz) else _strength_graph(A, theta, comp)
+        t1 = time.perf_counter()
         agg, n_agg = aggregate(S)
+        _log(f"  strength {t1-t0:.2f}s aggregate {time.perf_counter()-t1:.2f}s -> {n_agg}")
         if n_agg >= n or n_agg == 0:  # no coarsening possible
             break
         live = np.nonzero(agg >= 0)[0]
         cnt = np.bincount(agg[live], minlength=n_agg).astype(np.float64)
         T = sp.csr_matrix((1.0 / np.sqrt(cnt[agg[live]]), (live, agg[live])), shape=(n, n_agg))
-        DA = sp.diags(inv_diag) @ A
-        P = (T - (omega / lam) * (DA @ T)).tocsr()
+        AT = _spgemm(A, T)
+        P = (T - (omega / lam) * (sp.diags(inv_diag) @ AT)).tocsr()
+        del AT
         P.sort_indices()
         R = P.T.tocsr()
         R.sort_indices()
-        Ac = (R @ (A @ P)).tocsr()
+        Ac = _spgemm(R, _spgemm(A, P))
         Ac.sort_indices()
         L.P, L.R = P, R
         if comp is not None:

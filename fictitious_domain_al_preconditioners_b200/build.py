@@ -36,14 +36,13 @@ def build(force: bool = False, verbose: bool = False, with_nccl: bool | None = N
         nvcc_path(),
         "-gencode", "arch=compute_100a,code=sm_100a",
         "-O3", "-lineinfo", "-std=c++17",
-        "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function",
+        "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function,-fopenmp",
         "-ccbin", "/usr/bin/g++",
         "-shared", "-o", LIB,
     ]
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    if with_nccl:
-        cmd += ["-DFDAL_WITH_NCCL", "-lnccl"]
+    cmd += ["-lgomp", "-ldl"]
     cmd += srcs
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

@@ -63,6 +63,7 @@ class ALConfig:
     device: int = 0
     use_graphs: bool = True
     exact_mass_max_its: int = 0
+    block_size: int = 1
     outer: SolverControl = field(default_factory=lambda: ReductionControl(1000, 1e-10, 1e-12))
     inner: SolverControl = field(default_factory=lambda: SolverControl(100, 1e-2))
     mass: SolverControl = field(default_factory=lambda: SolverControl(100, 1e-6))
@@ -82,6 +83,8 @@ class ALConfig:
             self.device,
             int(self.use_graphs),
             self.exact_mass_max_its,
+            self.block_size,
+            0,
             self.outer.c(),
             self.inner.c(),
             self.mass.c(),

@@ -109,6 +109,11 @@ struct DevCsr {
   int4 *desc = nullptr;
   int nblk = 0;
   bool stream_ok = false;
+  // BSR copy (node-interleaved vector blocks): replaces the scalar arrays in the SpMV kernels
+  BsrDev bsr;
+  int bsr_b = 1;
+  bool use_bsr = false;
+  long long bsr_nblocks = 0;
   // multi-GPU
   bool dist_rows = false;  // rows are a partition: fused reductions need an all-reduce
   bool has_plan = false;
@@ -202,7 +207,7 @@ struct fdal_ctx {
   double *t_m0 = nullptr, *t_m1 = nullptr, *t_m2 = nullptr, *t_mw = nullptr;  // m-vectors
   double *t_n0 = nullptr;                                     // n0-vector
   double *t_p0 = nullptr, *t_p1 = nullptr;                    // n1-vectors
-  double *t_N0 = nullptr, *t_N1 = nullptr;                    // N-vectors (API staging)
+  double *t_N0 = nullptr, *t_N1 = nullptr, *t_N2 = nullptr;   // N-vectors (API staging)
   double *V = nullptr, *Z = nullptr, *d_h = nullptr, *d_y = nullptr;
   double *mr_u[3] = {nullptr, nullptr, nullptr}, *mr_m[3] = {nullptr, nullptr, nullptr}, *mr_v = nullptr;
   char *flush_buf = nullptr;
@@ -275,7 +280,84 @@ static int choose_tpr(double avg) {
   return 16;
 }
 
-static int upload_csr(fdal_ctx *c, const HostCsr &h, DevCsr &d) {
+// CSR -> BSR with B x B blocks (block-row SoA value layout, see k_bsr_spmv).  Returns false
+// (and leaves d untouched) when blocking would store too many explicit zeros.
+static int build_bsr(fdal_ctx *c, const HostCsr &h, int b, DevCsr &d, bool *done) {
+  *done = false;
+  if (b < 2 || b > 3 || h.nr % b || h.nc % b || h.owned_cols() % b || h.nr == 0) return FDAL_OK;
+  const int64_t nbr = h.nr / b;
+  std::vector<int> brp((size_t)nbr + 1, 0);
+#pragma omp parallel
+  {
+    std::vector<int> tmp;
+#pragma omp for schedule(dynamic, 2048)
+    for (int64_t I = 0; I < nbr; ++I) {
+      tmp.clear();
+      for (int r = 0; r < b; ++r)
+        for (int k = h.rp[I * b + r]; k < h.rp[I * b + r + 1]; ++k) tmp.push_back(h.ci[k] / b);
+      std::sort(tmp.begin(), tmp.end());
+      brp[(size_t)I + 1] = (int)(std::unique(tmp.begin(), tmp.end()) - tmp.begin());
+    }
+  }
+  int64_t nblk = 0;
+  for (int64_t I = 0; I < nbr; ++I) {
+    nblk += brp[(size_t)I + 1];
+    if (nblk >= (int64_t)std::numeric_limits<int>::max() / (b * b)) return FDAL_OK;
+    brp[(size_t)I + 1] = (int)nblk;
+  }
+  if ((double)nblk * b * b > 1.35 * (double)h.nnz) return FDAL_OK;  // too much zero fill: stay scalar
+  std::vector<int> bcj((size_t)nblk);
+  std::vector<double> bv((size_t)nblk * b * b, 0.0);
+#pragma omp parallel
+  {
+    std::vector<int> tmp;
+#pragma omp for schedule(dynamic, 2048)
+    for (int64_t I = 0; I < nbr; ++I) {
+      tmp.clear();
+      for (int r = 0; r < b; ++r)
+        for (int k = h.rp[I * b + r]; k < h.rp[I * b + r + 1]; ++k) tmp.push_back(h.ci[k] / b);
+      std::sort(tmp.begin(), tmp.end());
+      tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+      const int k0 = brp[(size_t)I];
+      const int nb = (int)tmp.size();
+      for (int k = 0; k < nb; ++k) bcj[(size_t)k0 + k] = tmp[k];
+      double *vb = bv.data() + (size_t)k0 * b * b;
+      for (int r = 0; r < b; ++r)
+        for (int k = h.rp[I * b + r]; k < h.rp[I * b + r + 1]; ++k) {
+          const int J = h.ci[k] / b, q = h.ci[k] % b;
+          const int pos = (int)(std::lower_bound(tmp.begin(), tmp.end(), J) - tmp.begin());
+          vb[(size_t)(r * b + q) * nb + pos] += h.v[k];
+        }
+    }
+  }
+  int *drp = nullptr, *dcj = nullptr;
+  double *dv = nullptr;
+  int st;
+  if ((st = dmalloc(c, &drp, (size_t)nbr + 1))) return st;
+  if ((st = dmalloc(c, &dcj, (size_t)nblk))) return st;
+  if ((st = dmalloc(c, &dv, (size_t)nblk * b * b))) return st;
+  CU(cudaMemcpyAsync(drp, brp.data(), ((size_t)nbr + 1) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(dcj, bcj.data(), (size_t)nblk * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(dv, bv.data(), (size_t)nblk * b * b * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  d.bsr.nbrows = (int)nbr;
+  d.bsr.rp = drp;
+  d.bsr.cj = dcj;
+  d.bsr.v = dv;
+  const double avg = (double)nblk / (double)nbr;
+  d.bsr.tpr = avg <= 6 ? 2 : avg <= 24 ? 4 : 8;
+  if (const char *e = getenv("FDAL_BSR_TPR")) {
+    const int t = atoi(e);
+    if (t == 2 || t == 4 || t == 8 || t == 16) d.bsr.tpr = t;
+  }
+  d.bsr_b = b;
+  d.bsr_nblocks = nblk;
+  d.use_bsr = true;
+  *done = true;
+  return FDAL_OK;
+}
+
+static int upload_csr(fdal_ctx *c, const HostCsr &h, DevCsr &d, int bsr_b = 1) {
   if (h.nnz >= (int64_t)std::numeric_limits<int>::max() || h.nr >= (int64_t)std::numeric_limits<int>::max()) {
     set_err(c, "matrix with %lld nnz exceeds the 32-bit row_ptr of this build", (long long)h.nnz);
     return FDAL_ERR_UNSUPPORTED;
@@ -301,6 +383,10 @@ static int upload_csr(fdal_ctx *c, const HostCsr &h, DevCsr &d) {
   d.d.v = d.v;
   d.d.tpr = choose_tpr(h.nr ? (double)h.nnz / (double)h.nr : 1.0);
   d.set = true;
+  if (bsr_b > 1 && !getenv("FDAL_NO_BSR")) {
+    bool done = false;
+    if ((st = build_bsr(c, h, bsr_b, d, &done))) return st;
+  }
   if (h.has_plan) {
     d.has_plan = true;
     d.n_owned = (int)h.n_owned;
@@ -408,6 +494,34 @@ static void spmv_stream(fdal_ctx *c, const DevCsr &A, const double *x, const Dev
   c->launches++;
   if (red_out && A.dist_rows) allreduce(c, red_out, 1);
 }
+template <class Epi, bool TWO>
+static void spmv_bsr(fdal_ctx *c, const DevCsr &A, const double *x, const DevCsr *B2, const double *t2, Epi epi,
+                     double *red_out) {
+  const int tpr = A.bsr.tpr;
+  const int g = grid_rows(c, A.bsr.nbrows, tpr);
+  Reducer R = reducer(c, red_out);
+  XVec X = xv(A, x);
+  CsrDev b2 = B2 ? B2->d : CsrDev();
+#define FDAL_BSR_LAUNCH(BB, TT) k_bsr_spmv<BB, TT, Epi, TWO><<<g, kBlock, 0, c->stream>>>(A.bsr, X, b2, t2, epi, R)
+  if (A.bsr_b == 2) {
+    switch (tpr) {
+      case 2: FDAL_BSR_LAUNCH(2, 2); break;
+      case 4: FDAL_BSR_LAUNCH(2, 4); break;
+      case 16: FDAL_BSR_LAUNCH(2, 16); break;
+      default: FDAL_BSR_LAUNCH(2, 8); break;
+    }
+  } else {
+    switch (tpr) {
+      case 2: FDAL_BSR_LAUNCH(3, 2); break;
+      case 4: FDAL_BSR_LAUNCH(3, 4); break;
+      case 16: FDAL_BSR_LAUNCH(3, 16); break;
+      default: FDAL_BSR_LAUNCH(3, 8); break;
+    }
+  }
+#undef FDAL_BSR_LAUNCH
+  c->launches++;
+  if (red_out && A.dist_rows) allreduce(c, red_out, 1);
+}
 template <class Epi>
 static void spmv(fdal_ctx *c, const DevCsr &A, const double *x, Epi epi, double *red_out = nullptr) {
   halo_exchange(c, A, x);
@@ -416,6 +530,10 @@ static void spmv(fdal_ctx *c, const DevCsr &A, const double *x, Epi epi, double 
       cudaMemsetAsync(red_out, 0, sizeof(double), c->stream);
       if (A.dist_rows) allreduce(c, red_out, 1);
     }
+    return;
+  }
+  if (A.use_bsr) {
+    spmv_bsr<Epi, false>(c, A, x, nullptr, nullptr, epi, red_out);
     return;
   }
   if (A.stream_ok && c->prefer_stream) {
@@ -454,6 +572,10 @@ static void spmv2(fdal_ctx *c, const DevCsr &A, const double *x, const DevCsr &C
       cudaMemsetAsync(red_out, 0, sizeof(double), c->stream);
       if (A.dist_rows) allreduce(c, red_out, 1);
     }
+    return;
+  }
+  if (A.use_bsr) {
+    spmv_bsr<Epi, true>(c, A, x, &Ct, t, epi, red_out);
     return;
   }
   if (A.stream_ok && c->prefer_stream) {
@@ -667,9 +789,9 @@ static bool capture_graph(fdal_ctx *c, const std::function<void()> &enqueue, cud
   return true;
 }
 static bool graphs_enabled(const fdal_ctx *c) {
-  // NCCL calls can be captured, but keep the multi-rank path on plain launches unless asked
-  static const bool dist_graphs = getenv("FDAL_DIST_GRAPHS") != nullptr;
-  return c->cfg.use_graphs && (c->nranks <= 1 || dist_graphs);
+  // NCCL send/recv and all-reduce are captured into the graphs as well (verified on 2 GPUs)
+  static const bool no_dist_graphs = getenv("FDAL_NO_DIST_GRAPHS") != nullptr;
+  return c->cfg.use_graphs && (c->nranks <= 1 || !no_dist_graphs);
 }
 static void run_cg_body(fdal_ctx *c, CgWs &w, const OpFn &op, const OpFn &prec, bool capturable) {
   if (graphs_enabled(c) && capturable && w.graph_ok && !stream_is_capturing(c)) {
@@ -790,8 +912,21 @@ static void apply_winv_scaled(fdal_ctx *c, double a, const double *x, double *y,
   const int repeat = c->cfg.winv_mode == FDAL_WINV_EXACT_M ? 1 : 2;
   if (c->mass_cta_ws) {
     // whole fixed-count PCG (both applications of M^-1 for W = M^2) in one CTA
-    k_mass_pcg_cta<<<1, kMassCtaThreads, 0, c->stream>>>(c->dmat[FDAL_MAT_M].d, c->d_m_invdiag, c->mass_its_m, repeat,
-                                                         a, x, add, y, c->mass_cta_ws);
+    const int threads = (int)std::min<int64_t>(kMassCtaThreads, ((m + 31) / 32) * 32);
+    if (m <= kMassCtaSmemRows) {
+      const size_t sm = (size_t)4 * m * sizeof(double);
+      static bool attr_done = false;
+      if (!attr_done) {
+        cudaFuncSetAttribute(k_mass_pcg_cta<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(4 * kMassCtaSmemRows * sizeof(double)));
+        attr_done = true;
+      }
+      k_mass_pcg_cta<true><<<1, threads, sm, c->stream>>>(c->dmat[FDAL_MAT_M].d, c->d_m_invdiag, c->mass_its_m, repeat,
+                                                          a, x, add, y, c->mass_cta_ws);
+    } else {
+      k_mass_pcg_cta<false><<<1, threads, 0, c->stream>>>(c->dmat[FDAL_MAT_M].d, c->d_m_invdiag, c->mass_its_m,
+                                                          repeat, a, x, add, y, c->mass_cta_ws);
+    }
     c->launches++;
     return;
   }
@@ -1293,7 +1428,7 @@ static int prepare_amg(fdal_ctx *c, Amg &g, bool dist) {
     } else {
       L.n = (int)L.hA.nr;
     }
-    if ((st = upload_csr(c, L.hA, L.A))) return st;
+    if ((st = upload_csr(c, L.hA, L.A, (l == 0 && !coarsest && &g == &c->amg[0]) ? c->cfg.block_size : 1))) return st;
     L.A.dist_rows = dist;
     if (!coarsest) {
       if (!L.hP.set) {
@@ -1589,7 +1724,7 @@ int fdal_finalize(fdal_ctx *c) {
   if (is_stokes(c) && !c->hmat[FDAL_MAT_B].set) host_transpose(c->hmat[FDAL_MAT_BT], c->hmat[FDAL_MAT_B]);
   for (int id = 0; id < FDAL_MAT_COUNT; ++id)
     if (c->hmat[id].set) {
-      if ((st = upload_csr(c, c->hmat[id], c->dmat[id]))) return st;
+      if ((st = upload_csr(c, c->hmat[id], c->dmat[id], id == FDAL_MAT_A ? c->cfg.block_size : 1))) return st;
       // host copy no longer needed
       HostCsr &h = c->hmat[id];
       std::vector<int>().swap(h.ci);
@@ -1616,6 +1751,7 @@ int fdal_finalize(fdal_ctx *c) {
   if ((st = dvec(c, &c->t_p1, c->n1))) return st;
   if ((st = dvec(c, &c->t_N0, c->N))) return st;
   if ((st = dvec(c, &c->t_N1, c->N))) return st;
+  if ((st = dvec(c, &c->t_N2, c->N))) return st;
   if ((st = alloc_cg(c, c->cg11, c->n0))) return st;
   c->cg11.dist = D;
   c->cg11.n_dot = c->n0;
@@ -1822,8 +1958,7 @@ int fdal_apply_prec(fdal_ctx *c, const double *u, double *v, int inner_its[2]) {
   int st;
   c->its_a11 = c->its_a22 = 0;
   // apply_prec uses t_N0 (ideal variant): stage through V-independent buffers
-  double *du = c->t_N1, *dv = nullptr;
-  if ((st = dvec(c, &dv, c->N))) return st;
+  double *du = c->t_N1, *dv = c->t_N2;
   if ((st = h2d(c, du, u, c->N))) return st;
   st = apply_prec(c, du, dv);
   if (inner_its) {
@@ -1831,8 +1966,6 @@ int fdal_apply_prec(fdal_ctx *c, const double *u, double *v, int inner_its[2]) {
     inner_its[1] = c->its_a22;
   }
   int st2 = d2h(c, v, dv, c->N);
-  cudaFree(dv);
-  c->allocs.erase(std::find(c->allocs.begin(), c->allocs.end(), (void *)dv));
   if (st) set_err(c, "inner solver did not converge (SolverControl::NoConvergence)");
   return st ? st : st2;
 }
@@ -1882,20 +2015,24 @@ int fdal_solve_dev(fdal_ctx *c, const double *d_rhs, double *d_x, fdal_solve_inf
 int fdal_solve(fdal_ctx *c, const double *rhs, double *x, fdal_solve_info *info) {
   BEGIN_CALL(c);
   int st;
-  double *drhs = c->t_N1, *dx = nullptr;
-  if ((st = dvec(c, &dx, c->N))) return st;
+  double *drhs = c->t_N1, *dx = c->t_N2;
   if ((st = h2d(c, drhs, rhs, c->N))) return st;
   if ((st = h2d(c, dx, x, c->N))) return st;
   st = fdal_solve_dev(c, drhs, dx, info);
   int st2 = d2h(c, x, dx, c->N);
-  cudaFree(dx);
-  c->allocs.erase(std::find(c->allocs.begin(), c->allocs.end(), (void *)dx));
   return st ? st : st2;
 }
 
 // ---- measurement ----------------------------------------------------------------------
 static double csr_bytes(const CsrDev &A) {
   return 12.0 * (double)A.nnz + 4.0 * ((double)A.nrows + 1) + 8.0 * (double)A.ncols + 8.0 * (double)A.nrows;
+}
+// algorithmic bytes of one mat-vec with the storage actually used (BSR or CSR)
+static double mat_bytes(const DevCsr &A) {
+  if (!A.use_bsr) return csr_bytes(A.d);
+  const double b2 = (double)A.bsr_b * A.bsr_b;
+  return (8.0 * b2 + 4.0) * (double)A.bsr_nblocks + 4.0 * ((double)A.bsr.nbrows + 1) + 8.0 * (double)A.d.ncols +
+         8.0 * (double)A.d.nrows;
 }
 int fdal_time_kernel(fdal_ctx *c, int what, int param, int warmup, int reps, int flush_l2, double *avg_ms,
                      double *alg_bytes, int64_t *launches_per_rep) {
@@ -1914,11 +2051,11 @@ int fdal_time_kernel(fdal_ctx *c, int what, int param, int warmup, int reps, int
   switch (what) {
     case FDAL_TIME_SPMV_A:
       run = [&]() { spmv(c, A, x, EpiAssign{y, 1.0}); };
-      bytes = csr_bytes(A.d);
+      bytes = mat_bytes(A);
       break;
     case FDAL_TIME_AUG:
       run = [&]() { apply_aug11(c, x, y, nullptr); };
-      bytes = csr_bytes(A.d) + csr_bytes(c->dmat[FDAL_MAT_C].d) + 12.0 * (double)c->dmat[FDAL_MAT_CT].d.nnz +
+      bytes = mat_bytes(A) + csr_bytes(c->dmat[FDAL_MAT_C].d) + 12.0 * (double)c->dmat[FDAL_MAT_CT].d.nnz +
               4.0 * ((double)n0 + 1) + 16.0 * (double)c->m;
       break;
     case FDAL_TIME_VCYCLE: {
@@ -1930,7 +2067,7 @@ int fdal_time_kernel(fdal_ctx *c, int what, int param, int warmup, int reps, int
         const double nl = (double)L.n;
         const int deg = L.degree;
         // pre: zero step (3 vec) + (deg-1) fused steps; residual; R; P; post: deg fused steps
-        bytes += 24.0 * nl + (2 * deg - 1) * (csr_bytes(L.A.d) + 32.0 * nl) + (csr_bytes(L.A.d) + 8.0 * nl) +
+        bytes += 24.0 * nl + (2 * deg - 1) * (mat_bytes(L.A) + 32.0 * nl) + (mat_bytes(L.A) + 8.0 * nl) +
                  csr_bytes(L.R.d) + csr_bytes(L.P.d) + 8.0 * nl;
       }
       const double cn = (double)g.lev.back().n;
@@ -1943,7 +2080,7 @@ int fdal_time_kernel(fdal_ctx *c, int what, int param, int warmup, int reps, int
         EpiCheb<false> e{x, L.invd, L.xa, L.d, L.xb, 0.3, 0.7, 0};
         spmv(c, L.A, L.xa, e);
       };
-      bytes = csr_bytes(L.A.d) + 32.0 * (double)L.n;
+      bytes = mat_bytes(L.A) + 32.0 * (double)L.n;
     } break;
     case FDAL_TIME_DOT:
       run = [&]() { dot(c, N, x, y, c->d_scal); };

@@ -256,6 +256,73 @@ __global__ void __launch_bounds__(kBlock) k_spmv2(CsrDev A, XVec X, CsrDev Ct, c
   if (Epi::kReduce) reduce_finalize(contrib, R, 0, 1, smem);
 }
 
+// ---- BSR SpMV for node-interleaved vector-valued blocks (Stokes velocity, elasticity) ----
+// B x B dense blocks (B = 2, 3) share one column index: (8 B^2 + 4) bytes per block instead
+// of 12 B^2 for scalar CSR (-25 % / -30 % HBM traffic on the dominant fine-level matrix).
+// Values are stored per block row as B^2 planes of nb doubles ("block-row SoA"), so every
+// load instruction of a row group reads consecutive doubles.  Epilogues are the scalar ones,
+// called for the B rows of the block row.  TWO adds a scalar CSR matrix with the same scalar
+// rows (Ct) in the same pass: y = A x + Ct t.
+struct BsrDev {
+  int nbrows = 0;
+  const int *rp = nullptr;    // [nbrows + 1] block-row pointer
+  const int *cj = nullptr;    // [nblocks] block column
+  const double *v = nullptr;  // per block row: B*B planes of (rp[I+1]-rp[I]) doubles
+  int tpr = 8;
+};
+
+template <int B, int TPR, class Epi, bool TWO>
+__global__ void __launch_bounds__(kBlock) k_bsr_spmv(BsrDev A, XVec X, CsrDev C2, const double *__restrict__ t2, Epi epi,
+                                                      Reducer R) {
+  __shared__ double smem[32];
+  constexpr int rows_per_block = kBlock / TPR;
+  const int lane = threadIdx.x & (TPR - 1);
+  const int local_row = threadIdx.x / TPR;
+  double contrib = 0.0;
+  for (long long base = (long long)blockIdx.x * rows_per_block; base < A.nbrows;
+       base += (long long)gridDim.x * rows_per_block) {
+    const long long I = base + local_row;
+    double s[B];
+#pragma unroll
+    for (int r = 0; r < B; ++r) s[r] = 0.0;
+    if (I < A.nbrows) {
+      const int k0 = __ldg(A.rp + I), k1 = __ldg(A.rp + I + 1);
+      const int nb = k1 - k0;
+      const double *vb = A.v + (size_t)k0 * (B * B);
+      for (int k = lane; k < nb; k += TPR) {
+        const int c = __ldg(A.cj + k0 + k) * B;
+        const double *xp = c < X.n_owned ? X.x + c : X.halo + (c - X.n_owned);
+        double xj[B], a[B * B];
+#pragma unroll
+        for (int q = 0; q < B * B; ++q) a[q] = __ldg(vb + (size_t)q * nb + k);
+#pragma unroll
+        for (int q = 0; q < B; ++q) xj[q] = __ldg(xp + q);
+#pragma unroll
+        for (int r = 0; r < B; ++r)
+#pragma unroll
+          for (int q = 0; q < B; ++q) s[r] += a[r * B + q] * xj[q];
+      }
+      if (TWO) {
+#pragma unroll
+        for (int r = 0; r < B; ++r) {
+          const long long row = I * B + r;
+          const int c0 = __ldg(C2.rp + row), c1 = __ldg(C2.rp + row + 1);
+          for (int k = c0 + lane; k < c1; k += TPR) s[r] += __ldg(C2.v + k) * __ldg(t2 + __ldg(C2.ci + k));
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < B; ++r)
+#pragma unroll
+      for (int o = TPR >> 1; o > 0; o >>= 1) s[r] += __shfl_down_sync(0xffffffffu, s[r], o, TPR);
+    if (lane == 0 && I < A.nbrows) {
+#pragma unroll
+      for (int r = 0; r < B; ++r) contrib += epi((int)(I * B + r), s[r]);
+    }
+  }
+  if (Epi::kReduce) reduce_finalize(contrib, R, 0, 1, smem);
+}
+
 // ---- TMA-staged CSR SpMV ("stream" variant, the default) ---------------------------
 // The value / column arrays of a run of whole rows (a "chunk", <= kChunk non-zeros,
 // row-aligned, built once at upload) are one contiguous byte range each, so a single
@@ -477,15 +544,17 @@ __global__ void k_set_scalar(double *p, double v) { *p = v; }
 // twice (W^-1 = M^-1 M^-1, immersed_laplace.cc:875-876).  y = a * result (+ add).
 constexpr int kMassCtaThreads = 1024;
 constexpr int kMassCtaMaxRows = 16384;
+constexpr int kMassCtaSmemRows = 6144;  // 4 vectors of m doubles in shared memory up to here
 
-__device__ __forceinline__ double block_allsum_1024(double v, double *smem /*[33]*/) {
+// block-wide sum broadcast to every thread (blockDim.x multiple of 32, <= 1024)
+__device__ __forceinline__ double block_allsum(double v, double *smem /*[33]*/) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   v = warp_sum(v);
   __syncthreads();
   if (lane == 0) smem[w] = v;
   __syncthreads();
   if (w == 0) {
-    double t = lane < (kMassCtaThreads >> 5) ? smem[lane] : 0.0;
+    double t = lane < (int)(blockDim.x >> 5) ? smem[lane] : 0.0;
     t = warp_sum(t);
     if (lane == 0) smem[32] = t;
   }
@@ -493,56 +562,61 @@ __device__ __forceinline__ double block_allsum_1024(double v, double *smem /*[33
   return smem[32];
 }
 
+// SMEM: the four CG vectors live in dynamic shared memory (4 * m doubles), else in `ws`
+template <bool SMEM>
 __global__ void __launch_bounds__(kMassCtaThreads) k_mass_pcg_cta(CsrDev M, const double *__restrict__ invd, int its,
                                                                    int repeat, double a, const double *__restrict__ b,
                                                                    const double *__restrict__ add, double *y,
                                                                    double *ws /* 5 * m */) {
+  extern __shared__ __align__(16) double svec[];
   __shared__ double red[33];
   const int n = M.nrows;
-  double *x = ws, *r = ws + n, *p = ws + 2 * (size_t)n, *v = ws + 3 * (size_t)n, *bb = ws + 4 * (size_t)n;
-  const int tid = threadIdx.x;
+  double *base = SMEM ? svec : ws;
+  double *x = base, *r = base + n, *p = base + 2 * (size_t)n, *v = base + 3 * (size_t)n;
+  double *bb = ws + 4 * (size_t)n;
+  const int tid = threadIdx.x, nt = blockDim.x;
   for (int rep = 0; rep < repeat; ++rep) {
     const double *rhs = rep == 0 ? b : bb;
     double part = 0.0;
-    for (int i = tid; i < n; i += kMassCtaThreads) {
+    for (int i = tid; i < n; i += nt) {
       const double ri = rhs[i];
-      const double zi = invd[i] * ri;
+      const double zi = __ldg(invd + i) * ri;
       x[i] = 0.0;
       r[i] = ri;
       p[i] = zi;
       part += ri * zi;
     }
-    double rho = block_allsum_1024(part, red);
+    double rho = block_allsum(part, red);
     for (int it = 0; it < its; ++it) {
       part = 0.0;
-      for (int i = tid; i < n; i += kMassCtaThreads) {
+      for (int i = tid; i < n; i += nt) {
         double s = 0.0;
-        const int k1 = M.rp[i + 1];
-        for (int k = M.rp[i]; k < k1; ++k) s += M.v[k] * p[M.ci[k]];
+        const int k1 = __ldg(M.rp + i + 1);
+        for (int k = __ldg(M.rp + i); k < k1; ++k) s += __ldg(M.v + k) * p[__ldg(M.ci + k)];
         v[i] = s;
         part += p[i] * s;
       }
-      const double pv = block_allsum_1024(part, red);
+      const double pv = block_allsum(part, red);
       const double alpha = pv != 0.0 ? rho / pv : 0.0;
       part = 0.0;
-      for (int i = tid; i < n; i += kMassCtaThreads) {
+      for (int i = tid; i < n; i += nt) {
         x[i] += alpha * p[i];
         const double ri = r[i] - alpha * v[i];
         r[i] = ri;
-        part += ri * ri * invd[i];
+        part += ri * ri * __ldg(invd + i);
       }
-      const double rho_new = block_allsum_1024(part, red);
+      const double rho_new = block_allsum(part, red);
       const double beta = rho != 0.0 ? rho_new / rho : 0.0;
       rho = rho_new;
-      for (int i = tid; i < n; i += kMassCtaThreads) p[i] = invd[i] * r[i] + beta * p[i];
+      for (int i = tid; i < n; i += nt) p[i] = __ldg(invd + i) * r[i] + beta * p[i];
       __syncthreads();
     }
     if (rep + 1 < repeat) {
-      for (int i = tid; i < n; i += kMassCtaThreads) bb[i] = x[i];
+      for (int i = tid; i < n; i += nt) bb[i] = x[i];
       __syncthreads();
     }
   }
-  for (int i = tid; i < n; i += kMassCtaThreads) y[i] = a * x[i] + (add ? add[i] : 0.0);
+  for (int i = tid; i < n; i += nt) y[i] = a * x[i] + (add ? add[i] : 0.0);
 }
 
 // y = a x + b y   (a, b host scalars; x may alias y only if a-term unused)

@@ -52,16 +52,28 @@ class DistCsr:
     plan: HaloPlan | None  # None: column space is replicated / fully local
 
 
-def localize(A: sp.csr_matrix, row_off: np.ndarray, col_off: np.ndarray, rank: int) -> DistCsr:
+def _node_complete(cols: np.ndarray, bs: int) -> np.ndarray:
+    """All components of every node touched by `cols` (BSR needs whole nodes in the halo)."""
+    if bs <= 1:
+        return np.unique(cols)
+    nodes = np.unique(cols // bs)
+    return (nodes[:, None] * bs + np.arange(bs, dtype=nodes.dtype)[None, :]).reshape(-1)
+
+
+def localize(A: sp.csr_matrix, row_off: np.ndarray, col_off: np.ndarray, rank: int, col_bs: int = 1) -> DistCsr:
     """Rows row_off[rank]:row_off[rank+1] of the (renumbered) global matrix with a halo plan
-    over the column space partitioned by col_off."""
+    over the column space partitioned by col_off.  col_bs > 1: the column space is
+    node-interleaved with col_bs components per node and halos hold whole nodes."""
     nranks = len(row_off) - 1
     A = A.tocsr()
+    if nranks == 1:  # nothing to cut: the whole matrix, empty plan
+        z = np.zeros(1, dtype=np.int32)
+        return DistCsr(A, HaloPlan(A.shape[1], 0, z, np.empty(0, np.int32), z.copy(), np.empty(0, np.int64)))
     c0, c1 = int(col_off[rank]), int(col_off[rank + 1])
     sub = A[int(row_off[rank]): int(row_off[rank + 1])].tocsr()
     cols = sub.indices.astype(np.int64)
     owned = (cols >= c0) & (cols < c1)
-    halo_globals = np.unique(cols[~owned])
+    halo_globals = _node_complete(cols[~owned], col_bs)
     newcol = np.empty_like(cols)
     newcol[owned] = cols[owned] - c0
     newcol[~owned] = (c1 - c0) + np.searchsorted(halo_globals, cols[~owned])
@@ -75,7 +87,9 @@ def localize(A: sp.csr_matrix, row_off: np.ndarray, col_off: np.ndarray, rank: i
             send_lists.append(np.empty(0, dtype=np.int64))
             continue
         subq = A[int(row_off[q]): int(row_off[q + 1])]
-        cq = np.unique(subq.indices)
+        cq = subq.indices.astype(np.int64)
+        q0, q1 = int(col_off[q]), int(col_off[q + 1])
+        cq = _node_complete(cq[(cq < q0) | (cq >= q1)], col_bs)
         mine = cq[(cq >= c0) & (cq < c1)]
         send_lists.append(mine - c0)
     send_counts = np.array([s.size for s in send_lists], dtype=np.int32)
@@ -90,9 +104,11 @@ def block0_order(prob) -> tuple[np.ndarray, int]:
     interleaved node-major so that a contiguous range is a spatial slab holding all
     components of its nodes."""
     n = prob.A.shape[0]
+    if prob.meta.get("node_major"):
+        return None, int(prob.meta["block_size"])  # already node-interleaved: identity
     comp = prob.amg_comp.get(b.AMG_A11)
     if comp is None:
-        return np.arange(n, dtype=np.int64), 1
+        return None, 1
     dim = int(comp.max()) + 1
     ns = n // dim
     node = np.arange(ns, dtype=np.int64)
@@ -104,6 +120,8 @@ def coarse_order(P: sp.csr_matrix, fine_off: np.ndarray):
     """Ownership of the coarse unknowns: a coarse unknown lives where the fine row with the
     largest weight in its column of P lives.  Returns new->old order and the offsets."""
     nranks = len(fine_off) - 1
+    if nranks == 1:
+        return None, np.array([0, P.shape[1]], dtype=np.int64)
     Pc = P.tocsc()
     nc = Pc.shape[1]
     owner = np.zeros(nc, dtype=np.int64)
@@ -156,12 +174,14 @@ class LocalProblem:
     order1: np.ndarray | None = None
     sizes_global: tuple = ()
     sizes_local: tuple = ()
+    block_size: int = 1
 
     # ---- vectors ---------------------------------------------------------------------
     def scatter(self, x_global: np.ndarray) -> np.ndarray:
         """Global block vector -> this rank's local vector [block0_loc | block1_loc/rep | rep]."""
         n0 = self.sizes_global[0]
-        parts = [x_global[:n0][self.order0][self.off0[self.rank]: self.off0[self.rank + 1]]]
+        x0 = x_global[:n0] if self.order0 is None else x_global[:n0][self.order0]
+        parts = [x0[self.off0[self.rank]: self.off0[self.rank + 1]]]
         rest = x_global[n0:]
         if self.off1 is not None:
             n1 = self.sizes_global[1]
@@ -176,7 +196,10 @@ class LocalProblem:
         n0 = self.sizes_global[0]
         out = np.zeros(sum(self.sizes_global))
         b0 = np.concatenate([v[: self.off0[r + 1] - self.off0[r]] for r, v in enumerate(locals_)])
-        out[:n0][self.order0] = b0
+        if self.order0 is None:
+            out[:n0] = b0
+        else:
+            out[:n0][self.order0] = b0
         if self.off1 is not None:
             n1 = self.sizes_global[1]
             b1 = np.concatenate([
@@ -193,6 +216,8 @@ class LocalProblem:
 
 def _perm(A, row_order, col_order):
     A = A.tocsr()
+    if row_order is None and col_order is None:
+        return A
     if row_order is not None:
         A = A[row_order]
     if col_order is not None:
@@ -202,7 +227,7 @@ def _perm(A, row_order, col_order):
     return A
 
 
-def distribute_hierarchy(H, order0, off0, rank, nranks) -> LocalHierarchy:
+def distribute_hierarchy(H, order0, off0, rank, nranks, bs: int = 1) -> LocalHierarchy:
     levels = []
     order_f, off_f = order0, off0
     nl = len(H.levels)
@@ -212,11 +237,13 @@ def distribute_hierarchy(H, order0, off0, rank, nranks) -> LocalHierarchy:
         order_c, off_c = coarse_order(_perm(L.P, order_f, None), off_f)
         Pp = _perm(L.P, order_f, order_c)
         Rp = _perm(L.R if L.R is not None else L.P.T, order_c, order_f)
+        lbs = bs if l == 0 else 1
         levels.append(LocalLevel(
-            A=localize(Aperm, off_f, off_f, rank),
+            A=localize(Aperm, off_f, off_f, rank, lbs),
             P=localize(Pp, off_f, off_c, rank),
-            R=localize(Rp, off_c, off_f, rank),
-            inv_diag=None if L.inv_diag is None else L.inv_diag[order_f][off_f[rank]: off_f[rank + 1]],
+            R=localize(Rp, off_c, off_f, rank, lbs),
+            inv_diag=None if L.inv_diag is None else
+            (L.inv_diag if order_f is None else L.inv_diag[order_f])[off_f[rank]: off_f[rank + 1]],
             lambda_max=L.lambda_max,
         ))
         order_f, off_f = order_c, off_c
@@ -235,7 +262,8 @@ def distribute_problem(prob, hierarchies: dict, rank: int, nranks: int) -> Local
                       sizes_global=prob.sizes, winv_diag=prob.winv_diag)
     rep_off = np.array([0] + [m] * nranks, dtype=np.int64)  # unused: replicated spaces have no plan
     A = _perm(prob.A, order0, order0)
-    lp.mats[b.MAT_A] = localize(A, off0, off0, rank)
+    lp.block_size = bs
+    lp.mats[b.MAT_A] = localize(A, off0, off0, rank, bs)
     Ct = _perm(prob.Ct, order0, None)
     lp.mats[b.MAT_CT] = DistCsr(Ct[off0[rank]: off0[rank + 1]].tocsr(), None)
     C = sp.csr_matrix(Ct.T)
@@ -249,7 +277,7 @@ def distribute_problem(prob, hierarchies: dict, rank: int, nranks: int) -> Local
         lp.order1, lp.off1 = order1, off1
         Bt = _perm(prob.Bt, order0, order1)
         lp.mats[b.MAT_BT] = localize(Bt, off0, off1, rank)
-        lp.mats[b.MAT_B] = localize(sp.csr_matrix(Bt.T), off1, off0, rank)
+        lp.mats[b.MAT_B] = localize(sp.csr_matrix(Bt.T), off1, off0, rank, bs)
         lp.mats[b.MAT_MP] = localize(_perm(prob.Mp, order1, order1), off1, off1, rank)
         lp.sizes_local = (n_loc, int(off1[rank + 1] - off1[rank]), m)
     elif kind == b.KIND_LAPLACE:
@@ -259,14 +287,16 @@ def distribute_problem(prob, hierarchies: dict, rank: int, nranks: int) -> Local
         lp.sizes_local = (n_loc, m, m)
     for which, H in hierarchies.items():
         if which == b.AMG_A11:
-            lp.amg[which] = distribute_hierarchy(H, order0, off0, rank, nranks)
+            lp.amg[which] = distribute_hierarchy(H, order0, off0, rank, nranks, bs)
         else:  # immersed block: replicated hierarchy
             lp.amg[which] = H
     return lp
 
 
-def setup_local_context(ctx, lp: LocalProblem, uid: bytes):
-    """Hand this rank's LocalProblem to its ALContext (after ``comm_init``) and finalize."""
+def setup_local_context(ctx, lp: LocalProblem, uid: bytes = bytes(128)):
+    """Hand this rank's LocalProblem to its ALContext (after ``comm_init``) and finalize.
+    With a single rank this is simply the node-interleaved (BSR-ready) renumbering of the
+    problem; ``ctx.config.block_size`` should then be ``lp.block_size``."""
     ctx.comm_init(uid, lp.rank, lp.nranks)
     for mid, dc in lp.mats.items():
         ctx.set_csr(mid, dc.local)

@@ -417,6 +417,136 @@ def immersed_laplace(
     return prob
 
 
+# ----------------------------------------------------------------------------- fast velocity block
+def velocity_block_tensor(nel: int, dim: int, gamma_grad_div: float, bnd_s: np.ndarray, device=None,
+                          interleaved: bool = False) -> sp.csr_matrix:
+    """(grad u, grad v) + gamma_gd (div u, div v) on the Q2^dim tensor grid with the Dirichlet
+    rows / columns already eliminated — the same matrix ``apply_dirichlet(bmat(kron ...))``
+    builds, assembled by index arithmetic on torch tensors (on the GPU when there is one:
+    at 10^9 non-zeros scipy's kron/bmat needs minutes and several copies of the matrix).
+    All d*d blocks share one sparsity pattern (the tensor product of the 1-D Q2 pattern), so
+    the pattern is sorted into CSR order once and every block is a product of 1-D values."""
+    import torch
+
+    if device is None:
+        device = "cuda" if torch.cuda.is_available() else "cpu"
+    h = 1.0 / nel
+    n1 = 2 * nel + 1
+    ns = n1**dim
+    K2, M2, D10 = (fe1d(nel, h, 2, 2, 1, 1), fe1d(nel, h, 2, 2), fe1d(nel, h, 2, 2, 1, 0))
+    pat = (abs(K2) + abs(M2) + abs(D10) + abs(D10.T)).tocoo()
+    order = np.lexsort((pat.col, pat.row))
+    r1 = torch.from_numpy(pat.row[order].astype(np.int64)).to(device)
+    c1 = torch.from_numpy(pat.col[order].astype(np.int64)).to(device)
+    dense = {"K": K2.toarray(), "M": M2.toarray(), "D": D10.toarray(), "Dt": D10.T.toarray()}
+    v1 = {k: torch.from_numpy(np.ascontiguousarray(a[pat.row[order], pat.col[order]])).to(device) for k, a in dense.items()}
+    nn = r1.numel()
+
+    def tensor_index(t1):  # flattened tensor-product index, slowest dimension first
+        out = t1
+        for _ in range(dim - 1):
+            out = (out[:, None] * n1 + t1[None, :]).reshape(-1)
+        return out
+
+    row3 = tensor_index(r1)
+    col3 = tensor_index(c1)
+    perm = torch.argsort(row3 * ns + col3)
+    row3 = row3[perm]
+    col3 = col3[perm]
+    bnd = torch.from_numpy(bnd_s).to(device)
+    interior = ~(bnd[row3] | bnd[col3])
+    diag_keep = interior | (row3 == col3)
+
+    def block_vals(names):  # names[k]: factor of dimension k (0 = x, fastest)
+        out = v1[names[dim - 1]]
+        for k in range(dim - 2, -1, -1):
+            out = (out[:, None] * v1[names[k]][None, :]).reshape(-1)
+        return out[perm]
+
+    lap = None
+    for k in range(dim):
+        t = block_vals(["K" if kk == k else "M" for kk in range(dim)])
+        lap = t if lap is None else lap + t
+    if interleaved:
+        # node-major numbering (row = node*dim + c): all d*d blocks of an interior row have
+        # the same pattern, so entry j of block (c,d) sits at indptr[row] + j*dim + d; a
+        # boundary row keeps only its diagonal
+        rows_i, cols_i = row3[interior], col3[interior]
+        cnt_int = torch.bincount(rows_i, minlength=ns)
+        blkptr = torch.zeros(ns + 1, dtype=torch.int64, device=device)
+        blkptr[1:] = torch.cumsum(cnt_int, 0)
+        j = torch.arange(rows_i.numel(), device=device) - blkptr[rows_i]
+        row_cnt = torch.where(bnd, torch.ones_like(cnt_int), cnt_int * dim)
+        row_cnt = row_cnt.repeat_interleave(dim)
+        n = dim * ns
+        indptr = torch.zeros(n + 1, dtype=torch.int64, device=device)
+        indptr[1:] = torch.cumsum(row_cnt, 0)
+        nnz = int(indptr[-1].item())
+        indices = torch.empty(nnz, dtype=torch.int32, device=device)
+        data = torch.empty(nnz, dtype=torch.float64, device=device)
+        bd = (row3 == col3) & bnd[row3]
+        rows_b = row3[bd]
+        for c in range(dim):
+            base = indptr[rows_i * dim + c] + j * dim
+            for d in range(dim):
+                if c == d:
+                    v = lap + gamma_grad_div * block_vals(["K" if kk == c else "M" for kk in range(dim)])
+                    pb = indptr[rows_b * dim + c]
+                    indices[pb] = (rows_b * dim + c).to(torch.int32)
+                    data[pb] = v[bd]
+                else:
+                    v = gamma_grad_div * block_vals(["D" if kk == c else ("Dt" if kk == d else "M") for kk in range(dim)])
+                indices[base + d] = (cols_i * dim + d).to(torch.int32)
+                data[base + d] = v[interior]
+                del v
+            del base
+        A = sp.csr_matrix((data.cpu().numpy(), indices.cpu().numpy(),
+                           indptr.cpu().numpy().astype(np.int64 if nnz >= 2**31 - 1 else np.int32)), shape=(n, n))
+        A.has_sorted_indices = True
+        return A
+    # per component row block: entries of blocks d = 0..dim-1, merged into CSR order
+    cnt = []
+    rows_k, cols_k, vals_k = [], [], []
+    for c in range(dim):
+        for d in range(dim):
+            if c == d:
+                v = lap + gamma_grad_div * block_vals(["K" if kk == c else "M" for kk in range(dim)])
+                keep = diag_keep
+            else:
+                v = gamma_grad_div * block_vals(["D" if kk == c else ("Dt" if kk == d else "M") for kk in range(dim)])
+                keep = interior
+            rows_k.append(row3[keep])
+            cols_k.append(col3[keep])
+            vals_k.append(v[keep])
+            cnt.append(torch.bincount(rows_k[-1], minlength=ns))
+            del v
+    del lap
+    n = dim * ns
+    row_cnt = torch.cat([sum(cnt[c * dim + d] for d in range(dim)) for c in range(dim)])
+    indptr = torch.zeros(n + 1, dtype=torch.int64, device=device)
+    indptr[1:] = torch.cumsum(row_cnt, 0)
+    nnz = int(indptr[-1].item())
+    indices = torch.empty(nnz, dtype=torch.int32, device=device)
+    data = torch.empty(nnz, dtype=torch.float64, device=device)
+    for c in range(dim):
+        off = torch.zeros(ns, dtype=torch.int64, device=device)
+        for d in range(dim):
+            k = c * dim + d
+            blkptr = torch.zeros(ns + 1, dtype=torch.int64, device=device)
+            blkptr[1:] = torch.cumsum(cnt[k], 0)
+            rk = rows_k[k]
+            pos = indptr[c * ns + rk] + off[rk] + (torch.arange(rk.numel(), device=device) - blkptr[rk])
+            indices[pos] = (cols_k[k] + d * ns).to(torch.int32)
+            data[pos] = vals_k[k]
+            off = off + cnt[k]
+            rows_k[k] = cols_k[k] = vals_k[k] = None
+            del pos, rk, blkptr
+    A = sp.csr_matrix((data.cpu().numpy(), indices.cpu().numpy(), indptr.cpu().numpy().astype(np.int64 if nnz >= 2**31 - 1 else np.int32)),
+                      shape=(n, n))
+    A.has_sorted_indices = True
+    return A
+
+
 # ----------------------------------------------------------------------------- C2 / C4: Stokes
 def stokes_immersed_boundary(
     dim: int = 2,
@@ -429,6 +559,8 @@ def stokes_immersed_boundary(
     diag_minres: bool = False,
     nq_coupling: int | None = None,
     build_amg_matrix: bool = True,
+    fast: bool | None = None,
+    numbering: str = "component",
 ) -> Problem:
     """3x3 system of stokes_immersed_boundary with ``Solver = IBStokesAL``
     (parameters_stokes.prm in 2-D, parameters_stokes_3d.prm in 3-D;
@@ -451,28 +583,46 @@ def stokes_immersed_boundary(
     def K(facs):
         return kron_all([facs[k] for k in order])
 
-    lap = None
-    for k in dims:
-        t = K({kk: (K2 if kk == k else M2) for kk in dims})
-        lap = t if lap is None else lap + t
-    blocks = [[None] * dim for _ in range(dim)]
-    for c in dims:
-        for d in dims:
-            if c == d:
-                gd = K({kk: (K2 if kk == c else M2) for kk in dims})
-                blocks[c][d] = lap + gamma_grad_div * gd
-            else:
-                gd = K({kk: (D10 if kk == c else (D10.T.tocsr() if kk == d else M2)) for kk in dims})
-                blocks[c][d] = gamma_grad_div * gd
-    A = _csr(sp.bmat(blocks, format="csr"))
-    del blocks, lap
+    bnd_s = boundary_mask(n1, dim)
+    bnd = np.tile(bnd_s, dim)
+    if fast is None:
+        fast = ns * dim >= 200_000
+    import time as _time
+
+    _t0 = _time.perf_counter()
+    node_major = numbering == "node"
+    # new -> old order of the node-major numbering (row = node*dim + c)
+    node_order = (np.arange(ns, dtype=np.int64)[:, None] + ns * np.arange(dim, dtype=np.int64)[None, :]).reshape(-1)
+    if fast:
+        A = velocity_block_tensor(nel, dim, gamma_grad_div, bnd_s, interleaved=node_major)
+        from .amg_setup import _log
+
+        _log(f"velocity block nel={nel} dim={dim}: nnz={A.nnz} in {_time.perf_counter()-_t0:.2f}s")
+    else:
+        lap = None
+        for k in dims:
+            t = K({kk: (K2 if kk == k else M2) for kk in dims})
+            lap = t if lap is None else lap + t
+        blocks = [[None] * dim for _ in range(dim)]
+        for c in dims:
+            for d in dims:
+                if c == d:
+                    gd = K({kk: (K2 if kk == c else M2) for kk in dims})
+                    blocks[c][d] = lap + gamma_grad_div * gd
+                else:
+                    gd = K({kk: (D10 if kk == c else (D10.T.tocsr() if kk == d else M2)) for kk in dims})
+                    blocks[c][d] = gamma_grad_div * gd
+        A = _csr(sp.bmat(blocks, format="csr"))
+        del blocks, lap
+        A = apply_dirichlet(A, bnd)
+        if node_major:
+            A = _csr(A[node_order][:, node_order])
     Bblk = [-K({kk: (E if kk == c else F) for kk in dims}) for c in dims]
     B = _csr(sp.hstack(Bblk, format="csr"))
     Mp = _csr(kron_all([Mq1] * dim))
-    bnd_s = boundary_mask(n1, dim)
-    bnd = np.tile(bnd_s, dim)
-    A = apply_dirichlet(A, bnd)
     Bt = zero_rows(_csr(B.T), bnd)
+    if node_major:
+        Bt = _csr(Bt[node_order])
     n_u, n_p = A.shape[0], Mp.shape[0]
     # immersed boundary
     if dim == 2:
@@ -499,10 +649,14 @@ def stokes_immersed_boundary(
     # vector-valued: background component-wise, immersed interleaved (j*dim + c)
     sel = [sp.csr_matrix((np.ones(ms), (np.arange(ms), np.arange(ms) * dim + c)), shape=(ms, ms * dim)) for c in dims]
     Ct = _csr(sp.vstack([Cs @ sel[c] for c in dims], format="csr"))
+    if node_major:
+        Ct = _csr(Ct[node_order])
     M = _csr(sum(sel[c].T @ Ms @ sel[c] for c in dims))
     m = M.shape[0]
     mass_u = kron_all([M2] * dim) @ np.ones(ns)
     fvec = np.concatenate([fval[c] * np.where(bnd_s, 0.0, mass_u) for c in dims])
+    if node_major:
+        fvec = fvec[node_order]
     gnod = np.tile(gval, ms)
     gvec = M @ gnod
     cfg = ALConfig(
@@ -537,8 +691,10 @@ def stokes_immersed_boundary(
         # (utilities.h:112-331; the AL gamma is used for grad-div, SURVEY Q7 — equal here)
         prob.amg_matrix[b.AMG_A11] = _csr(A + gamma * (Ct @ sp.diags(winv) @ Ct.T))
         prob.amg_theta[b.AMG_A11] = 0.02  # utilities.h:314
-        prob.amg_comp[b.AMG_A11] = np.repeat(np.arange(dim, dtype=np.int32), ns)
-    prob.meta = dict(h=h, n_u=n_u, n_p=n_p, m=m, nel=nel, dim=dim, r_emb=r_emb)
+        comp = np.repeat(np.arange(dim, dtype=np.int32), ns)
+        prob.amg_comp[b.AMG_A11] = comp[node_order] if node_major else comp
+    prob.meta = dict(h=h, n_u=n_u, n_p=n_p, m=m, nel=nel, dim=dim, r_emb=r_emb, node_major=node_major,
+                     block_size=dim)
     return prob
 
 

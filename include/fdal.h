@@ -144,6 +144,10 @@ typedef struct fdal_config {
   int32_t device;      /* CUDA device ordinal                                 */
   int32_t use_graphs;  /* replay the V-cycle / CG iteration as CUDA graphs    */
   int32_t exact_mass_max_its; /* cap for the device mass solve (0 = default)  */
+  int32_t block_size;  /* > 1: block0 unknowns are node-interleaved with this many
+                          components per node (Stokes velocity dim, elasticity 3): A and
+                          the finest AMG operator are stored as BSR (dim-blocked SpMV) */
+  int32_t reserved0;
   fdal_control outer;  /* outer FGMRES / MinRes control                       */
   fdal_control inner;  /* inner CG on A_gamma (and on A22_gamma)              */
   fdal_control mass;   /* Mp^-1 CG control: (100, 1e-6)                       */

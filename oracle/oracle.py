@@ -25,7 +25,9 @@ _api = None
 
 def build(force=False):
     src = os.path.join(_HERE, "fdal_oracle.c")
-    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(src):
+    hdr = os.path.join(_HERE, "..", "include", "fdal.h")
+    newest = max(os.path.getmtime(src), os.path.getmtime(hdr))
+    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < newest:
         subprocess.run(["make", "-C", _HERE], check=True, capture_output=True)
     return LIB_PATH
 

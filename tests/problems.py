@@ -17,6 +17,8 @@ CASES = {
     "stokes2d_diag": (syn.stokes_immersed_boundary, dict(dim=2, nel=32, diagonal_mass=True)),
     "stokes2d_minres": (syn.stokes_immersed_boundary, dict(dim=2, nel=16, diagonal_mass=True, diag_minres=True)),
     "stokes3d_diag": (syn.stokes_immersed_boundary, dict(dim=3, nel=8)),
+    "stokes3d_node": (syn.stokes_immersed_boundary, dict(dim=3, nel=8, numbering="node")),
+    "stokes2d_node": (syn.stokes_immersed_boundary, dict(dim=2, nel=32, diagonal_mass=True, numbering="node")),
     "elliptic_modified": (syn.elliptic_interface, dict(cycle=2)),
     "elliptic_modified_diag": (syn.elliptic_interface, dict(cycle=2, diagonal_inverse=True)),
     "elliptic_modified_fixed": (syn.elliptic_interface, dict(cycle=2, fixed_iterations=True)),

@@ -44,7 +44,7 @@ def test_binding_table_matches_header():
 def test_struct_sizes_match_the_c_side():
     # fdal_control: 2*int32 + 2*double ; fdal_config: 13 int32/double fields + 3 controls
     assert ctypes.sizeof(b.Control) == 24
-    assert ctypes.sizeof(b.Config) == 8 + 24 + 8 * 4 + 3 * 24
+    assert ctypes.sizeof(b.Config) == 8 + 24 + 10 * 4 + 3 * 24
     assert ctypes.sizeof(b.SolveInfo) == 8 * 4 + 3 * 8 + 8 + 8 * b.MAX_HISTORY
     assert ctypes.sizeof(b.CsrView) == 48
 

@@ -83,15 +83,32 @@ def dist_vcycle(LH, bvec, rank, nranks, l=0):
     return cheb(x, False)
 
 
+def _ord(v, order):
+    return v if order is None else v[order]
+
+
 def _worker(rank, nranks, port, case, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=nranks)
     try:
+        _worker_body(rank, nranks, case, q)
+    except Exception as e:  # surface the failure instead of a queue timeout
+        import traceback
+
+        q.put((rank, {"error": traceback.format_exc()[-1500:]}))
+    finally:
+        dist.destroy_process_group()
+
+
+def _worker_body(rank, nranks, case, q):
+    if True:
         from tests.test_oracle_known_answers import vcycle_ref
 
         if case == "stokes":
             prob = syn.stokes_immersed_boundary(dim=2, nel=8, diagonal_mass=True)
+        elif case == "stokes_node":
+            prob = syn.stokes_immersed_boundary(dim=2, nel=8, diagonal_mass=True, numbering="node")
         else:
             prob = syn.immersed_laplace(r_bg=4)
         H = syn.build_hierarchies(prob, max_coarse=40)
@@ -107,15 +124,15 @@ def _worker(rank, nranks, port, case, q):
         lam = X[-m:]
         y0 = dist_spmv(lp.mats[b.MAT_A], x0, rank, nranks) + lp.mats[b.MAT_CT].local @ lam
         cx = allreduce(lp.mats[b.MAT_C].local @ x0)
-        ref0 = (prob.A @ X[:n] + prob.Ct @ lam)[lp.order0][lp.off0[rank]: lp.off0[rank + 1]]
+        ref0 = _ord(prob.A @ X[:n] + prob.Ct @ lam, lp.order0)[lp.off0[rank]: lp.off0[rank + 1]]
         res["A"] = float(np.abs(y0 - ref0).max())
         res["C"] = float(np.abs(cx - prob.Ct.T @ X[:n]).max())
-        if case == "stokes":
+        if case.startswith("stokes"):
             n1l = lp.sizes_local[1]
             n_p = prob.Bt.shape[1]
             x1 = xl[n0l: n0l + n1l]
             yb = dist_spmv(lp.mats[b.MAT_BT], x1, rank, nranks)
-            refb = (prob.Bt @ X[n: n + n_p])[lp.order0][lp.off0[rank]: lp.off0[rank + 1]]
+            refb = _ord(prob.Bt @ X[n: n + n_p], lp.order0)[lp.off0[rank]: lp.off0[rank + 1]]
             res["Bt"] = float(np.abs(yb - refb).max())
             yB = dist_spmv(lp.mats[b.MAT_B], x0, rank, nranks)
             res["B"] = float(np.abs(yB - (prob.Bt.T @ X[:n])[lp.off1[rank]: lp.off1[rank + 1]]).max())
@@ -131,15 +148,13 @@ def _worker(rank, nranks, port, case, q):
         # distributed V-cycle == serial V-cycle
         LH = lp.amg[b.AMG_A11]
         z = dist_vcycle(LH, x0, rank, nranks)
-        zref = vcycle_ref(H[b.AMG_A11], X[:n])[lp.order0][lp.off0[rank]: lp.off0[rank + 1]]
+        zref = _ord(vcycle_ref(H[b.AMG_A11], X[:n]), lp.order0)[lp.off0[rank]: lp.off0[rank + 1]]
         res["vcycle"] = float(np.abs(z - zref).max() / np.abs(zref).max())
         res["levels"] = len(LH.levels)
         q.put((rank, res))
-    finally:
-        dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("case", ["laplace", "stokes"])
+@pytest.mark.parametrize("case", ["laplace", "stokes", "stokes_node"])
 def test_two_rank_partition_matches_serial(case):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -152,6 +167,7 @@ def test_two_rank_partition_matches_serial(case):
         p.join(timeout=60)
         assert p.exitcode == 0
     for rank, res in out:
+        assert "error" not in res, res.get("error")
         assert res.pop("levels") >= 1
         for k, v in res.items():
             assert v < 1e-11, (rank, k, v)
