@@ -308,6 +308,8 @@ static int build_bsr(fdal_ctx *c, const HostCsr &h, int b, DevCsr &d, bool *done
   if ((double)nblk * b * b > 1.35 * (double)h.nnz) return FDAL_OK;  // too much zero fill: stay scalar
   std::vector<int> bcj((size_t)nblk);
   std::vector<double> bv((size_t)nblk * b * b, 0.0);
+  // blocks stored contiguously (AoS): measured 25-40 % faster on B200 than per-row planes (profiles/)
+  const bool aos = getenv("FDAL_BSR_PLANES") == nullptr;
 #pragma omp parallel
   {
     std::vector<int> tmp;
@@ -326,7 +328,10 @@ static int build_bsr(fdal_ctx *c, const HostCsr &h, int b, DevCsr &d, bool *done
         for (int k = h.rp[I * b + r]; k < h.rp[I * b + r + 1]; ++k) {
           const int J = h.ci[k] / b, q = h.ci[k] % b;
           const int pos = (int)(std::lower_bound(tmp.begin(), tmp.end(), J) - tmp.begin());
-          vb[(size_t)(r * b + q) * nb + pos] += h.v[k];
+          if (aos)
+            vb[(size_t)pos * b * b + (r * b + q)] += h.v[k];
+          else
+            vb[(size_t)(r * b + q) * nb + pos] += h.v[k];
         }
     }
   }
@@ -345,7 +350,8 @@ static int build_bsr(fdal_ctx *c, const HostCsr &h, int b, DevCsr &d, bool *done
   d.bsr.cj = dcj;
   d.bsr.v = dv;
   const double avg = (double)nblk / (double)nbr;
-  d.bsr.tpr = avg <= 6 ? 2 : avg <= 24 ? 4 : 8;
+  d.bsr.tpr = avg <= 6 ? 2 : avg <= 24 ? 4 : 16;
+  d.bsr.aos = aos ? 1 : 0;
   if (const char *e = getenv("FDAL_BSR_TPR")) {
     const int t = atoi(e);
     if (t == 2 || t == 4 || t == 8 || t == 16) d.bsr.tpr = t;
@@ -502,7 +508,13 @@ static void spmv_bsr(fdal_ctx *c, const DevCsr &A, const double *x, const DevCsr
   Reducer R = reducer(c, red_out);
   XVec X = xv(A, x);
   CsrDev b2 = B2 ? B2->d : CsrDev();
-#define FDAL_BSR_LAUNCH(BB, TT) k_bsr_spmv<BB, TT, Epi, TWO><<<g, kBlock, 0, c->stream>>>(A.bsr, X, b2, t2, epi, R)
+#define FDAL_BSR_LAUNCH(BB, TT)                                                                     \
+  do {                                                                                              \
+    if (A.bsr.aos)                                                                                  \
+      k_bsr_spmv<BB, TT, Epi, TWO, true><<<g, kBlock, 0, c->stream>>>(A.bsr, X, b2, t2, epi, R);    \
+    else                                                                                            \
+      k_bsr_spmv<BB, TT, Epi, TWO, false><<<g, kBlock, 0, c->stream>>>(A.bsr, X, b2, t2, epi, R);   \
+  } while (0)
   if (A.bsr_b == 2) {
     switch (tpr) {
       case 2: FDAL_BSR_LAUNCH(2, 2); break;

@@ -419,7 +419,7 @@ def immersed_laplace(
 
 # ----------------------------------------------------------------------------- fast velocity block
 def velocity_block_tensor(nel: int, dim: int, gamma_grad_div: float, bnd_s: np.ndarray, device=None,
-                          interleaved: bool = False) -> sp.csr_matrix:
+                          interleaved: bool = False, p: int = 2, length: float = 1.0, terms=None) -> sp.csr_matrix:
     """(grad u, grad v) + gamma_gd (div u, div v) on the Q2^dim tensor grid with the Dirichlet
     rows / columns already eliminated — the same matrix ``apply_dirichlet(bmat(kron ...))``
     builds, assembled by index arithmetic on torch tensors (on the GPU when there is one:
@@ -430,10 +430,17 @@ def velocity_block_tensor(nel: int, dim: int, gamma_grad_div: float, bnd_s: np.n
 
     if device is None:
         device = "cuda" if torch.cuda.is_available() else "cpu"
-    h = 1.0 / nel
-    n1 = 2 * nel + 1
+    h = length / nel
+    n1 = p * nel + 1
     ns = n1**dim
-    K2, M2, D10 = (fe1d(nel, h, 2, 2, 1, 1), fe1d(nel, h, 2, 2), fe1d(nel, h, 2, 2, 1, 0))
+    K2, M2, D10 = (fe1d(nel, h, p, p, 1, 1), fe1d(nel, h, p, p), fe1d(nel, h, p, p, 1, 0))
+    if terms is None:
+        # Stokes velocity block: (grad u, grad v) + gamma_gd (div u, div v)
+        def terms(c, d):
+            if c == d:
+                t = [(1.0, ["K" if kk == k else "M" for kk in range(dim)]) for k in range(dim)]
+                return t + [(gamma_grad_div, ["K" if kk == c else "M" for kk in range(dim)])]
+            return [(gamma_grad_div, ["D" if kk == c else ("Dt" if kk == d else "M") for kk in range(dim)])]
     pat = (abs(K2) + abs(M2) + abs(D10) + abs(D10.T)).tocoo()
     order = np.lexsort((pat.col, pat.row))
     r1 = torch.from_numpy(pat.row[order].astype(np.int64)).to(device)
@@ -463,10 +470,13 @@ def velocity_block_tensor(nel: int, dim: int, gamma_grad_div: float, bnd_s: np.n
             out = (out[:, None] * v1[names[k]][None, :]).reshape(-1)
         return out[perm]
 
-    lap = None
-    for k in range(dim):
-        t = block_vals(["K" if kk == k else "M" for kk in range(dim)])
-        lap = t if lap is None else lap + t
+    def block(c, d):
+        out = None
+        for coef, names in terms(c, d):
+            t = coef * block_vals(names)
+            out = t if out is None else out + t
+        return out
+
     if interleaved:
         # node-major numbering (row = node*dim + c): all d*d blocks of an interior row have
         # the same pattern, so entry j of block (c,d) sits at indptr[row] + j*dim + d; a
@@ -489,13 +499,11 @@ def velocity_block_tensor(nel: int, dim: int, gamma_grad_div: float, bnd_s: np.n
         for c in range(dim):
             base = indptr[rows_i * dim + c] + j * dim
             for d in range(dim):
+                v = block(c, d)
                 if c == d:
-                    v = lap + gamma_grad_div * block_vals(["K" if kk == c else "M" for kk in range(dim)])
                     pb = indptr[rows_b * dim + c]
                     indices[pb] = (rows_b * dim + c).to(torch.int32)
                     data[pb] = v[bd]
-                else:
-                    v = gamma_grad_div * block_vals(["D" if kk == c else ("Dt" if kk == d else "M") for kk in range(dim)])
                 indices[base + d] = (cols_i * dim + d).to(torch.int32)
                 data[base + d] = v[interior]
                 del v
@@ -509,18 +517,13 @@ def velocity_block_tensor(nel: int, dim: int, gamma_grad_div: float, bnd_s: np.n
     rows_k, cols_k, vals_k = [], [], []
     for c in range(dim):
         for d in range(dim):
-            if c == d:
-                v = lap + gamma_grad_div * block_vals(["K" if kk == c else "M" for kk in range(dim)])
-                keep = diag_keep
-            else:
-                v = gamma_grad_div * block_vals(["D" if kk == c else ("Dt" if kk == d else "M") for kk in range(dim)])
-                keep = interior
+            v = block(c, d)
+            keep = diag_keep if c == d else interior
             rows_k.append(row3[keep])
             cols_k.append(col3[keep])
             vals_k.append(v[keep])
             cnt.append(torch.bincount(rows_k[-1], minlength=ns))
             del v
-    del lap
     n = dim * ns
     row_cnt = torch.cat([sum(cnt[c * dim + d] for d in range(dim)) for c in range(dim)])
     indptr = torch.zeros(n + 1, dtype=torch.int64, device=device)
@@ -781,6 +784,124 @@ def elliptic_interface(
     prob.amg_theta[b.AMG_A11] = 1e-3  # utilities.h:731
     prob.amg_theta[b.AMG_A22] = 1e-4
     prob.meta = dict(h=h, h_imm=h_imm, n_bg=n, m=m, cycle=cycle, beta2=beta2)
+    return prob
+
+
+# ----------------------------------------------------------------------------- C5: elasticity
+def _elasticity_terms(lam: float, mu: float, dim: int):
+    """Blocks of  2 mu eps(u):eps(v) + lam div u div v  for u = phi_j e_d, v = phi_i e_c
+    (utilities.h:377-427, ElasticityUtilities::assemble_elasticity)."""
+
+    def terms(c, d):
+        if c == d:
+            t = [(mu, ["K" if kk == k else "M" for kk in range(dim)]) for k in range(dim)]
+            return t + [(mu + lam, ["K" if kk == c else "M" for kk in range(dim)])]
+        return [
+            (mu, ["D" if kk == d else ("Dt" if kk == c else "M") for kk in range(dim)]),  # d_d phi_i d_c phi_j
+            (lam, ["D" if kk == c else ("Dt" if kk == d else "M") for kk in range(dim)]),  # d_c phi_i d_d phi_j
+        ]
+
+    return terms
+
+
+def elasticity_interface(
+    cycle: int = 1,
+    lam_bg: float = 2.0,
+    mu_bg: float = 1.0,
+    lam_imm: float = 20.0,
+    mu_imm: float = 10.0,
+    gamma_fluid: float = 10.0,
+    gamma_solid: float = 1e-2,
+    diagonal_inverse: bool = False,
+    nq_coupling: int = 3,
+    nel_bg: int | None = None,
+    nel_imm: int | None = None,
+) -> Problem:
+    """Vector-valued elliptic interface problem of parameters_elliptic_interface/elasticity.prm
+    (the driver elliptic_interface_elasticity.cc is missing from the reference; the
+    block structure is the 3x3 modified-AL system of elliptic_interface.cc with the blocks of
+    ElasticityUtilities, utilities.h:376-589): Q1^3 on [-1.25,1.25]^3 at refinement 2+cycle,
+    box inclusion (-0.65,-0.3,-0.4)-(0.65,0.3,0.4) at refinement ``cycle``.  Both spaces are
+    numbered node-major (3 components per node) so the background block runs as BSR-3."""
+    dim = 3
+    nel = nel_bg or 2 ** (2 + cycle)
+    nim = nel_imm or 2**cycle
+    L = 2.5
+    n1 = nel + 1
+    bnd_s = boundary_mask(n1, dim)
+    A1 = velocity_block_tensor(nel, dim, 0.0, bnd_s, interleaved=True, p=1, length=L,
+                               terms=_elasticity_terms(lam_bg, mu_bg, dim))
+    lo = np.array([-0.65, -0.3, -0.4])
+    hi = np.array([0.65, 0.3, 0.4])
+    # immersed tensor grid: nim cells per direction of the box (anisotropic cells)
+    m1 = nim + 1
+    xi = [np.linspace(lo[k], hi[k], m1) for k in range(dim)]
+    xq, wq = gauss01(nq_coupling)
+    pts_1d = [(xi[k][:-1, None] + (xi[k][1:] - xi[k][:-1])[:, None] * xq[None, :]).reshape(-1) for k in range(dim)]
+    w_1d = [((xi[k][1:] - xi[k][:-1])[:, None] * wq[None, :]).reshape(-1) for k in range(dim)]
+    Z, Y, X = np.meshgrid(pts_1d[2], pts_1d[1], pts_1d[0], indexing="ij")
+    pts = np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1)
+    Wz, Wy, Wx = np.meshgrid(w_1d[2], w_1d[1], w_1d[0], indexing="ij")
+    JxW = (Wx * Wy * Wz).ravel()
+    Phi = background_shape_matrix(pts, nel, -1.25, 1.25, 1)
+    # immersed shape functions: the same tensor-product evaluation on the box, per direction scaling
+    unit = (pts - lo[None, :]) / (hi - lo)[None, :]
+    Psi = background_shape_matrix(unit, nim, 0.0, 1.0, 1)
+    W = sp.diags(JxW)
+    Cs = zero_rows(_csr(Phi.T @ W @ Psi), bnd_s)
+    Ms = _csr(Psi.T @ W @ Psi)
+    I3 = sp.identity(dim, format="csr")
+    Ct = _csr(sp.kron(Cs, I3, format="csr"))
+    M = _csr(sp.kron(Ms, I3, format="csr"))
+    # immersed stiffness with the coefficient jump, anisotropic cells: assemble per direction
+    hs = (hi - lo) / nim
+    K1 = [fe1d(nim, hs[k], 1, 1, 1, 1) for k in range(dim)]
+    M1 = [fe1d(nim, hs[k], 1, 1) for k in range(dim)]
+    D1 = [fe1d(nim, hs[k], 1, 1, 1, 0) for k in range(dim)]
+    fac = {"K": K1, "M": M1, "D": D1, "Dt": [d.T.tocsr() for d in D1]}
+    terms2 = _elasticity_terms(lam_imm - lam_bg, mu_imm - mu_bg, dim)
+    ms = m1**dim
+    rows, cols, vals = [], [], []
+    for c in range(dim):
+        for d in range(dim):
+            blk = None
+            for coef, names in terms2(c, d):
+                t = coef * kron_all([fac[names[k]][k] for k in (2, 1, 0)])
+                blk = t if blk is None else blk + t
+            blk = blk.tocoo()
+            rows.append(blk.row * dim + c)
+            cols.append(blk.col * dim + d)
+            vals.append(blk.data)
+    A2 = _csr(sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(dim * ms, dim * ms)))
+    n, m = Ct.shape
+    h_imm = float(np.linalg.norm(hs))
+    g1, g2 = gamma_fluid / h_imm**2, gamma_solid / h_imm**2
+    mass_bg = kron_all([fe1d(nel, L / nel, 1, 1)] * dim) @ np.ones(n1**dim)
+    f1 = np.repeat(np.where(bnd_s, 0.0, mass_bg), dim) * 1.0  # f = 1
+    f2 = M @ np.ones(m) * 2.0  # f_2 = 2
+    cfg = ALConfig(
+        kind=b.KIND_ELLIPTIC_MODIFIED,
+        restart=50,
+        gamma=g1,
+        gamma2=g2,
+        inner=ReductionControl(10000, 1e-2, 1e-20),
+        outer=ReductionControl(1000, 1e-10, 1e-6),
+    )
+    prob = Problem(name=f"elasticity_c{cycle}", config=cfg, A=A1, A2=A2, Ct=Ct, M=M,
+                   rhs=np.concatenate([f1, f2, np.zeros(m)]), augment_rhs=False)
+    if diagonal_inverse:
+        cfg.winv_mode = b.WINV_DIAG
+        prob.winv_diag = _winv_diag_from(M, squared=False)
+    else:
+        cfg.winv_mode = b.WINV_EXACT_M
+    Vd = sp.diags(prob.winv_diag) if diagonal_inverse else sp.identity(m)
+    prob.amg_matrix[b.AMG_A11] = _csr(A1 + g1 * (Ct @ Vd @ Ct.T))
+    prob.amg_matrix[b.AMG_A22] = _csr(A2 + g2 * M)
+    prob.amg_theta[b.AMG_A11] = 1e-3  # utilities.h:572-574
+    prob.amg_theta[b.AMG_A22] = 1e-4
+    prob.amg_comp[b.AMG_A11] = np.tile(np.arange(dim, dtype=np.int32), n1**dim)  # constant modes
+    prob.amg_comp[b.AMG_A22] = np.tile(np.arange(dim, dtype=np.int32), ms)
+    prob.meta = dict(h=L / nel, h_imm=h_imm, n_bg=n, m=m, cycle=cycle, node_major=True, block_size=dim)
     return prob
 
 

@@ -6,7 +6,7 @@ import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402
-from fictitious_domain_al_preconditioners_b200 import ALContext, _binding as b, synthetic as syn  # noqa: E402
+from fictitious_domain_al_preconditioners_b200 import ALContext, _binding as b, partition as part, synthetic as syn  # noqa: E402
 
 wname = sys.argv[1] if len(sys.argv) > 1 else "stokes2d_diag"
 w = dict(bench.WORKLOADS[wname])
@@ -23,7 +23,9 @@ configs = [c.split(",") for c in os.environ.get("PROBE_CONFIGS", "").split(";") 
     ["FDAL_SPMV=stream", "FDAL_STREAM_CTAS=3"],
     ["FDAL_SPMV=stream", "FDAL_STREAM_CTAS=2"],
 ]
-KN = ("FDAL_SPMV", "FDAL_UNROLL", "FDAL_TPR", "FDAL_STREAM_CTAS")
+KN = ("FDAL_SPMV", "FDAL_UNROLL", "FDAL_TPR", "FDAL_STREAM_CTAS", "FDAL_NO_BSR", "FDAL_BSR_TPR", "FDAL_BSR_AOS")
+lp = part.distribute_problem(prob, H, 0, 1)
+prob.config.block_size = lp.block_size
 print(f"workload {wname} N={prob.n_dofs} nnz(A)={prob.A.nnz} levels={H[0].describe()}")
 for cfg in configs:
     for k in KN:
@@ -31,7 +33,7 @@ for cfg in configs:
     for kv in cfg:
         k, v = kv.split("=")
         os.environ[k] = v
-    ctx = syn.setup_context(ALContext(prob.config), prob, H)
+    ctx = part.setup_local_context(ALContext(prob.config), lp)
     row = {}
     for name, what in (("spmv_A", b.TIME_SPMV_A), ("cheb_fine", b.TIME_CHEB_FINE), ("aug", b.TIME_AUG),
                        ("vcycle", b.TIME_VCYCLE)):

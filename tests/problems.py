@@ -24,6 +24,8 @@ CASES = {
     "elliptic_modified_fixed": (syn.elliptic_interface, dict(cycle=2, fixed_iterations=True)),
     "elliptic_ideal": (syn.elliptic_interface, dict(cycle=2, modified=False, gamma_solid=10.0)),
     "elliptic_m2": (syn.elliptic_interface, dict(cycle=1, h_scaled=False, diagonal_inverse=True)),
+    "elasticity": (syn.elasticity_interface, dict(cycle=1)),
+    "elasticity_diag": (syn.elasticity_interface, dict(cycle=2, diagonal_inverse=True)),
 }
 
 

@@ -11,11 +11,12 @@ from fictitious_domain_al_preconditioners_b200 import partition as part
 from fictitious_domain_al_preconditioners_b200 import synthetic as syn
 
 from . import problems as P
+from .test_gpu_parity import _self_sensitivity
 
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name", ["stokes2d_diag", "stokes2d_exact", "stokes3d_diag", "stokes3d_node", "stokes2d_node"])
+@pytest.mark.parametrize("name", ["stokes2d_diag", "stokes2d_exact", "stokes3d_diag", "stokes3d_node", "stokes2d_node", "elasticity", "elasticity_diag"])
 def test_bsr_path_matches_oracle(name, oracle_mod):
     prob, H = P.get(name)
     lp = part.distribute_problem(prob, H, 0, 1)
@@ -40,13 +41,15 @@ def test_bsr_path_matches_oracle(name, oracle_mod):
     v, its = gpu.apply_prec(lp.scatter(u))
     vo, ito = ora.apply_prec(u)
     assert tuple(its) == tuple(ito)
-    assert P.relerr(lp.gather([v]), vo) < 1e-10
+    tol = max(1e-10, 50 * _self_sensitivity(lambda w: ora.apply_prec(w)[0], u, 2))
+    assert P.relerr(lp.gather([v]), vo) < tol
     rhs = P.rhs_of(ora, prob)
     xg, ig = gpu.solve(lp.scatter(rhs))
     xo, io = ora.solve(rhs)
     assert abs(ig.outer_iterations - io.outer_iterations) <= 1
     if ig.outer_iterations == io.outer_iterations:
-        assert P.relerr(lp.gather([xg]), xo) < 1e-10
+        tol = max(1e-10, 50 * _self_sensitivity(lambda w: ora.solve(w)[0], rhs, 4))
+        assert P.relerr(lp.gather([xg]), xo) < tol
     # the BSR kernels were the ones that ran
     ms, by, nl = gpu.time_kernel(b.TIME_SPMV_A, 0, warmup=1, reps=2, flush_l2=False)
     bs = lp.block_size
