@@ -1997,7 +1997,7 @@ int fdal_solve_dev(fdal_ctx *c, const double *d_rhs, double *d_x, fdal_solve_inf
   if (!info) info = &local;
   memset(info, 0, sizeof(*info));
   c->its_a11 = c->its_a22 = c->its_mass = c->n_inner_solves = 0;
-  const int64_t l0 = c->launches;
+  const int64_t l0 = c->launches, g0 = c->graph_launches;
   cudaEvent_t e0, e1;
   CU(cudaEventCreate(&e0));
   CU(cudaEventCreate(&e1));
@@ -2016,6 +2016,7 @@ int fdal_solve_dev(fdal_ctx *c, const double *d_rhs, double *d_x, fdal_solve_inf
   info->inner_solves = c->n_inner_solves;
   info->mass_iterations = c->its_mass;
   info->kernel_launches = c->launches - l0;
+  info->reserved = (int32_t)std::min<int64_t>(c->graph_launches - g0, std::numeric_limits<int32_t>::max());
   if (st == FDAL_ERR_INNER_NO_CONVERGENCE)
     set_err(c, "inner CG did not converge (SolverControl::NoConvergence)");
   else if (st == FDAL_ERR_OUTER_NO_CONVERGENCE)

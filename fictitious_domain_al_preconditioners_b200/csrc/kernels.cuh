@@ -553,30 +553,31 @@ constexpr int kMassCtaThreads = 1024;
 constexpr int kMassCtaMaxRows = 16384;
 constexpr int kMassCtaSmemRows = 6144;  // 4 vectors of m doubles in shared memory up to here
 
-// block-wide sum broadcast to every thread (blockDim.x multiple of 32, <= 1024)
-__device__ __forceinline__ double block_allsum(double v, double *smem /*[33]*/) {
+// block-wide sum broadcast to every thread with ONE __syncthreads: warp partials go to one
+// of two alternating shared buffers, then every warp re-reduces all partials redundantly
+// (blockDim.x multiple of 32, <= 1024).  `buf` must alternate between consecutive calls.
+__device__ __forceinline__ double block_allsum(double v, double *smem /*[2][32]*/, int buf) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  double *s = smem + buf * 32;
   v = warp_sum(v);
+  if (lane == 0) s[w] = v;
   __syncthreads();
-  if (lane == 0) smem[w] = v;
-  __syncthreads();
-  if (w == 0) {
-    double t = lane < (int)(blockDim.x >> 5) ? smem[lane] : 0.0;
-    t = warp_sum(t);
-    if (lane == 0) smem[32] = t;
-  }
-  __syncthreads();
-  return smem[32];
+  double t = lane < (int)(blockDim.x >> 5) ? s[lane] : 0.0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  return t;
 }
 
-// SMEM: the four CG vectors live in dynamic shared memory (4 * m doubles), else in `ws`
+// SMEM: the four CG vectors live in dynamic shared memory (4 * m doubles), else in `ws`.
+// Every thread owns the rows i = tid, tid + nt, ...: only the mat-vec reads other threads'
+// entries (of p), so one iteration needs three barriers (two inside the reductions).
 template <bool SMEM>
 __global__ void __launch_bounds__(kMassCtaThreads) k_mass_pcg_cta(CsrDev M, const double *__restrict__ invd, int its,
                                                                    int repeat, double a, const double *__restrict__ b,
                                                                    const double *__restrict__ add, double *y,
                                                                    double *ws /* 5 * m */) {
   extern __shared__ __align__(16) double svec[];
-  __shared__ double red[33];
+  __shared__ double red[64];
   const int n = M.nrows;
   double *base = SMEM ? svec : ws;
   double *x = base, *r = base + n, *p = base + 2 * (size_t)n, *v = base + 3 * (size_t)n;
@@ -593,7 +594,7 @@ __global__ void __launch_bounds__(kMassCtaThreads) k_mass_pcg_cta(CsrDev M, cons
       p[i] = zi;
       part += ri * zi;
     }
-    double rho = block_allsum(part, red);
+    double rho = block_allsum(part, red, 0);  // its barrier also publishes p
     for (int it = 0; it < its; ++it) {
       part = 0.0;
       for (int i = tid; i < n; i += nt) {
@@ -603,24 +604,23 @@ __global__ void __launch_bounds__(kMassCtaThreads) k_mass_pcg_cta(CsrDev M, cons
         v[i] = s;
         part += p[i] * s;
       }
-      const double pv = block_allsum(part, red);
+      const double pv = block_allsum(part, red, 1);
       const double alpha = pv != 0.0 ? rho / pv : 0.0;
       part = 0.0;
-      for (int i = tid; i < n; i += nt) {
+      for (int i = tid; i < n; i += nt) {  // own rows only
         x[i] += alpha * p[i];
         const double ri = r[i] - alpha * v[i];
         r[i] = ri;
         part += ri * ri * __ldg(invd + i);
       }
-      const double rho_new = block_allsum(part, red);
+      const double rho_new = block_allsum(part, red, 0);  // all mat-vec reads of p are done
       const double beta = rho != 0.0 ? rho_new / rho : 0.0;
       rho = rho_new;
       for (int i = tid; i < n; i += nt) p[i] = __ldg(invd + i) * r[i] + beta * p[i];
-      __syncthreads();
+      __syncthreads();  // p complete for the next mat-vec
     }
     if (rep + 1 < repeat) {
-      for (int i = tid; i < n; i += nt) bb[i] = x[i];
-      __syncthreads();
+      for (int i = tid; i < n; i += nt) bb[i] = x[i];  // own rows; re-read by the owner only
     }
   }
   for (int i = tid; i < n; i += nt) y[i] = a * x[i] + (add ? add[i] : 0.0);

@@ -162,7 +162,7 @@ typedef struct fdal_solve_info {
   int32_t inner_solves;      /* number of Aug_inv applications                */
   int32_t mass_iterations;   /* sum over Mp^-1 CG solves                      */
   int32_t n_history;         /* valid entries of residual_history             */
-  int32_t reserved;
+  int32_t reserved;          /* CUDA graph launches issued by the solve              */
   double initial_residual;
   double final_residual;
   double solve_ms;           /* device time of the solve (CUDA events)        */
