@@ -338,6 +338,13 @@ def run_ours(args, w, wname):
         except Exception as e:  # e.g. multidot without FGMRES basis
             kern[name] = {"error": str(e)}
     dom = kern.get("cheb_fine", {})
+    traffic = None
+    try:  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
+        if wname in tj and world == 1 and not args.nel and not args.no_bsr:
+            traffic = tj[wname]["traffic_bytes_per_launch"]
+    except Exception:
+        pass
     last = infos[-1]
     total_dofs = prob.n_dofs  # the whole (weak-scaled) job, all ranks together
     if rank == 0:
@@ -359,9 +366,10 @@ def run_ours(args, w, wname):
                     "ms_per_step": e2e_s * 1e3},
             "gpu_launches": int(sum(i.kernel_launches for i in infos)),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_spmv<TPR,EpiCheb> (fused Chebyshev step, finest AMG level)",
+            "roofline": {"bound": "hbm", "kernel": "fused Chebyshev step on the finest AMG level (k_bsr_spmv<B,TPR,EpiCheb> / k_spmv<TPR,EpiCheb>)",
                          "achieved": dom.get("GBps"), "peak": peak, "unit": "GB/s",
-                         "frac": dom.get("frac"), "traffic": None, "peak_source": peak_src},
+                         "frac": dom.get("frac"), "traffic": traffic, "algorithmic_bytes": dom.get("alg_bytes"),
+                         "peak_source": peak_src},
             "kernels": kern,
         }
         if not args.no_cpu and world == 1:

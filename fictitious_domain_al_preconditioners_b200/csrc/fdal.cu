@@ -189,6 +189,10 @@ struct fdal_ctx {
   fdal_config cfg;
   int sms = 148;
   cudaStream_t stream = nullptr;
+  // second stream: A x runs beside the single-CTA exact mass solve of the augmented apply
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool overlap_mass = false;
   HostCsr hmat[FDAL_MAT_COUNT];
   DevCsr dmat[FDAL_MAT_COUNT];
   std::vector<double> h_winv, h_mp_lumped;
@@ -221,7 +225,7 @@ struct fdal_ctx {
   int rank = 0, nranks = 1;
   ncclComm_t comm = nullptr;
   int64_t n_dot_outer = 0;
-  int stream_ctas_per_sm = 3, spmv_unroll = 4;
+  int stream_ctas_per_sm = 3, spmv_unroll = 4, bsr_unroll = 1;
   bool prefer_stream = false;
   int fail = 0;
   std::vector<void *> allocs;
@@ -510,10 +514,12 @@ static void spmv_bsr(fdal_ctx *c, const DevCsr &A, const double *x, const DevCsr
   CsrDev b2 = B2 ? B2->d : CsrDev();
 #define FDAL_BSR_LAUNCH(BB, TT)                                                                     \
   do {                                                                                              \
-    if (A.bsr.aos)                                                                                  \
-      k_bsr_spmv<BB, TT, Epi, TWO, true><<<g, kBlock, 0, c->stream>>>(A.bsr, X, b2, t2, epi, R);    \
-    else                                                                                            \
+    if (!A.bsr.aos)                                                                                 \
       k_bsr_spmv<BB, TT, Epi, TWO, false><<<g, kBlock, 0, c->stream>>>(A.bsr, X, b2, t2, epi, R);   \
+    else if (c->bsr_unroll > 1)                                                                     \
+      k_bsr_spmv<BB, TT, Epi, TWO, true, 2><<<g, kBlock, 0, c->stream>>>(A.bsr, X, b2, t2, epi, R); \
+    else                                                                                            \
+      k_bsr_spmv<BB, TT, Epi, TWO, true><<<g, kBlock, 0, c->stream>>>(A.bsr, X, b2, t2, epi, R);    \
   } while (0)
   if (A.bsr_b == 2) {
     switch (tpr) {
@@ -1002,6 +1008,22 @@ static void apply_aug11(fdal_ctx *c, const double *x, double *y, double *dot_out
       spmv(c, A, x, EpiDotX{y, x}, dot_out);
     else
       spmv(c, A, x, EpiAssign{y, 1.0});
+  } else if (c->overlap_mass && c->mass_cta_ws && c->nranks == 1 && !gd) {
+    // exact W^-1: the mass solve is ONE CTA for ~90 us.  Fork: y = A x on the second stream
+    // fills the other 147 SMs meanwhile; join: y += Ct t (+ fused x.y) over the few rows of Ct.
+    cudaEventRecord(c->ev_fork, c->stream);
+    cudaStreamWaitEvent(c->stream2, c->ev_fork, 0);
+    cudaStream_t main_stream = c->stream;
+    c->stream = c->stream2;
+    spmv(c, A, x, EpiAssign{y, 1.0});
+    c->stream = main_stream;
+    couple_phase1(c, x, c->cfg.gamma, nullptr, nullptr, c->t_m0);
+    cudaEventRecord(c->ev_join, c->stream2);
+    cudaStreamWaitEvent(c->stream, c->ev_join, 0);
+    if (dot_out)
+      spmv(c, c->dmat[FDAL_MAT_CT], c->t_m0, EpiAddDotX{y, x}, dot_out);
+    else
+      spmv(c, c->dmat[FDAL_MAT_CT], c->t_m0, EpiAdd{y, 1.0});
   } else {
     couple_phase1(c, x, c->cfg.gamma, nullptr, nullptr, c->t_m0);
     if (dot_out && !gd)
@@ -1548,9 +1570,17 @@ int fdal_create(fdal_ctx **out, const fdal_config *cfg) {
     return FDAL_ERR_CUDA;
   }
   cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, cfg->device);
+  if (cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+    delete c;
+    return FDAL_ERR_CUDA;
+  }
+  if (const char *e = getenv("FDAL_OVERLAP")) c->overlap_mass = atoi(e) != 0;
   // tuning knobs (measurement only; defaults are the shipped configuration)
   if (const char *e = getenv("FDAL_SPMV")) c->prefer_stream = strcmp(e, "stream") == 0;
   if (const char *e = getenv("FDAL_UNROLL")) c->spmv_unroll = atoi(e);
+  if (const char *e = getenv("FDAL_BSR_UNROLL")) c->bsr_unroll = atoi(e);
   if (const char *e = getenv("FDAL_STREAM_CTAS")) c->stream_ctas_per_sm = std::max(1, atoi(e));
   *out = c;
   return FDAL_OK;
@@ -1567,6 +1597,9 @@ void fdal_destroy(fdal_ctx *c) {
   for (void *p : c->allocs) cudaFree(p);
   if (c->comm) nccl_api()->CommDestroy(c->comm);
   if (c->h_scal) cudaFreeHost(c->h_scal);
+  if (c->stream2) cudaStreamDestroy(c->stream2);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }

@@ -145,6 +145,16 @@ struct EpiCouple {
     return 0.0;
   }
 };
+struct EpiAddDotX {  // y += A x ; reduce x_i * y_i  (joins the overlapped augmented apply)
+  double *y;
+  const double *x;
+  static constexpr bool kReduce = true;
+  __device__ double operator()(int i, double s) const {
+    const double yn = y[i] + s;
+    y[i] = yn;
+    return x[i] * yn;
+  }
+};
 struct EpiDotX {  // y = A x ; reduce x_i * y_i  (p.Ap of CG)
   double *y;
   const double *x;
@@ -273,7 +283,7 @@ struct BsrDev {
   int aos = 0;
 };
 
-template <int B, int TPR, class Epi, bool TWO, bool AOS>
+template <int B, int TPR, class Epi, bool TWO, bool AOS, int U = 1>
 __global__ void __launch_bounds__(kBlock) k_bsr_spmv(BsrDev A, XVec X, CsrDev C2, const double *__restrict__ t2, Epi epi,
                                                       Reducer R) {
   __shared__ double smem[32];
@@ -291,18 +301,27 @@ __global__ void __launch_bounds__(kBlock) k_bsr_spmv(BsrDev A, XVec X, CsrDev C2
       const int k0 = __ldg(A.rp + I), k1 = __ldg(A.rp + I + 1);
       const int nb = k1 - k0;
       const double *vb = A.v + (size_t)k0 * (B * B);
-      for (int k = lane; k < nb; k += TPR) {
-        const int c = __ldg(A.cj + k0 + k) * B;
-        const double *xp = c < X.n_owned ? X.x + c : X.halo + (c - X.n_owned);
-        double xj[B], a[B * B];
+      for (int kk = lane; kk < nb; kk += U * TPR) {
+        // U blocks per lane in flight: all loads of the U blocks are issued before any FMA
+        double xj[U][B], a[U][B * B];
 #pragma unroll
-        for (int q = 0; q < B * B; ++q) a[q] = AOS ? __ldg(vb + (size_t)k * (B * B) + q) : __ldg(vb + (size_t)q * nb + k);
+        for (int u = 0; u < U; ++u) {
+          const int k = kk + u * TPR;
+          const bool ok = k < nb;
+          const int c = (ok ? __ldg(A.cj + k0 + k) : 0) * B;
+          const double *xp = c < X.n_owned ? X.x + c : X.halo + (c - X.n_owned);
 #pragma unroll
-        for (int q = 0; q < B; ++q) xj[q] = __ldg(xp + q);
+          for (int q = 0; q < B * B; ++q)
+            a[u][q] = ok ? (AOS ? __ldg(vb + (size_t)k * (B * B) + q) : __ldg(vb + (size_t)q * nb + k)) : 0.0;
 #pragma unroll
-        for (int r = 0; r < B; ++r)
+          for (int q = 0; q < B; ++q) xj[u][q] = ok ? __ldg(xp + q) : 0.0;
+        }
 #pragma unroll
-          for (int q = 0; q < B; ++q) s[r] += a[r * B + q] * xj[q];
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int r = 0; r < B; ++r)
+#pragma unroll
+            for (int q = 0; q < B; ++q) s[r] += a[u][r * B + q] * xj[u][q];
       }
       if (TWO) {
 #pragma unroll
