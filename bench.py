@@ -216,6 +216,10 @@ def run_ours(args, w, wname):
     # torchrun pins OMP_NUM_THREADS=1; the host-side setup helpers (OpenMP SpGEMM, BSR
     # conversion) should share the box's cores between the ranks instead
     os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // max(1, world_env)))
+    if world_env > 1:
+        # every rank builds the hierarchy itself: keep the setup bit-reproducible across ranks
+        # (no GPU mat-vec in the eigenvalue estimate) so all ranks cut identical matrices
+        os.environ["FDAL_DETERMINISTIC_SETUP"] = "1"
     import torch
 
     from fictitious_domain_al_preconditioners_b200 import ALContext
@@ -244,6 +248,16 @@ def run_ours(args, w, wname):
     t0 = time.perf_counter()
     from fictitious_domain_al_preconditioners_b200 import partition as part
 
+    if world > 1:
+        # rank 0's Chebyshev eigenvalue estimates are authoritative (belt and braces)
+        import torch.distributed as dist
+
+        lam = [[L.lambda_max for L in H[k].levels] for k in sorted(H)]
+        box = [lam]
+        dist.broadcast_object_list(box, src=0)
+        for k, vals in zip(sorted(H), box[0]):
+            for L, v in zip(H[k].levels, vals):
+                L.lambda_max = v
     lp = part.distribute_problem(prob, H, rank, world)
     if not args.no_bsr:
         prob.config.block_size = lp.block_size

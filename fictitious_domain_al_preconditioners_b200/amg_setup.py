@@ -212,7 +212,7 @@ def estimate_lambda_max(A: sp.csr_matrix, inv_diag: np.ndarray, iters: int = 20)
     if n <= 3:
         M = (sp.diags(s) @ A @ sp.diags(s)).toarray()
         return float(np.max(np.linalg.eigvalsh(0.5 * (M + M.T))))
-    if _cuda_ok(A.nnz):
+    if _cuda_ok(A.nnz) and not os.environ.get("FDAL_DETERMINISTIC_SETUP"):
         import torch
 
         At = _to_torch_csr(A)

@@ -192,7 +192,7 @@ struct fdal_ctx {
   // second stream: A x runs beside the single-CTA exact mass solve of the augmented apply
   cudaStream_t stream2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  bool overlap_mass = false;
+  bool overlap_mass = true;  // FDAL_OVERLAP=0 switches the fork/join off
   HostCsr hmat[FDAL_MAT_COUNT];
   DevCsr dmat[FDAL_MAT_COUNT];
   std::vector<double> h_winv, h_mp_lumped;
@@ -1011,13 +1011,16 @@ static void apply_aug11(fdal_ctx *c, const double *x, double *y, double *dot_out
   } else if (c->overlap_mass && c->mass_cta_ws && c->nranks == 1 && !gd) {
     // exact W^-1: the mass solve is ONE CTA for ~90 us.  Fork: y = A x on the second stream
     // fills the other 147 SMs meanwhile; join: y += Ct t (+ fused x.y) over the few rows of Ct.
+    // C x first, then fork: the one-CTA mass kernel is enqueued BEFORE the grid-filling A x
+    // (whose persistent CTAs would otherwise hold every SM until they finish)
+    spmv(c, c->dmat[FDAL_MAT_C], x, EpiCouple{c->t_m1, nullptr, 1.0, nullptr, nullptr});
     cudaEventRecord(c->ev_fork, c->stream);
+    apply_winv_scaled(c, c->cfg.gamma, c->t_m1, c->t_m0);
     cudaStreamWaitEvent(c->stream2, c->ev_fork, 0);
     cudaStream_t main_stream = c->stream;
     c->stream = c->stream2;
     spmv(c, A, x, EpiAssign{y, 1.0});
     c->stream = main_stream;
-    couple_phase1(c, x, c->cfg.gamma, nullptr, nullptr, c->t_m0);
     cudaEventRecord(c->ev_join, c->stream2);
     cudaStreamWaitEvent(c->stream, c->ev_join, 0);
     if (dot_out)
@@ -1490,7 +1493,7 @@ static int prepare_amg(fdal_ctx *c, Amg &g, bool dist) {
       if (!L.h_invd.empty()) {
         CU(cudaMemcpyAsync(L.invd, L.h_invd.data(), (size_t)L.n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
       } else {
-        k_inv_diag_from_csr<<<(L.n + 255) / 256, 256, 0, c->stream>>>(L.n, L.A.rp, L.A.ci, L.A.v, L.invd);
+        k_inv_diag_from_csr<<<std::max(1, (L.n + 255) / 256), 256, 0, c->stream>>>(L.n, L.A.rp, L.A.ci, L.A.v, L.invd);
       }
       if ((st = dvec(c, &L.r, L.n))) return st;
       if ((st = dvec(c, &L.d, L.n))) return st;
@@ -1535,7 +1538,7 @@ static int need(fdal_ctx *c, int id, const char *name) {
 static int invdiag_of(fdal_ctx *c, const DevCsr &M, double **out) {
   int st = dvec(c, out, M.d.nrows);
   if (st) return st;
-  k_inv_diag_from_csr<<<(M.d.nrows + 255) / 256, 256, 0, c->stream>>>(M.d.nrows, M.rp, M.ci, M.v, *out);
+  k_inv_diag_from_csr<<<std::max(1, (M.d.nrows + 255) / 256), 256, 0, c->stream>>>(M.d.nrows, M.rp, M.ci, M.v, *out);
   return FDAL_OK;
 }
 

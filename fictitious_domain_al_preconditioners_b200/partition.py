@@ -117,23 +117,24 @@ def block0_order(prob) -> tuple[np.ndarray, int]:
 
 
 def coarse_order(P: sp.csr_matrix, fine_off: np.ndarray):
-    """Ownership of the coarse unknowns: a coarse unknown lives where the fine row with the
-    largest weight in its column of P lives.  Returns new->old order and the offsets."""
+    """Ownership of the coarse unknowns, from the sparsity PATTERN of P only: a coarse unknown
+    lives with the median fine row of its column.  Every rank derives the partition from its
+    own copy of the hierarchy, so the rule must not depend on floating-point values (an
+    arg-max over |P_ij| has ties that round differently when the setup ran on different
+    devices, which would give the ranks inconsistent halo plans and dead-lock the exchange).
+    Returns new->old order and the offsets."""
     nranks = len(fine_off) - 1
     if nranks == 1:
         return None, np.array([0, P.shape[1]], dtype=np.int64)
     Pc = P.tocsc()
+    Pc.sort_indices()
     nc = Pc.shape[1]
-    owner = np.zeros(nc, dtype=np.int64)
-    absd = np.abs(Pc.data)
-    # arg-max per column via a stable sort on (column, -|value|)
-    col_of = np.repeat(np.arange(nc), np.diff(Pc.indptr))
-    key = np.lexsort((-absd, col_of))
-    first = Pc.indptr[:-1]
-    has = np.diff(Pc.indptr) > 0
-    rows_max = np.zeros(nc, dtype=np.int64)
-    rows_max[has] = Pc.indices[key[first[has]]]
-    owner = np.searchsorted(fine_off, rows_max, side="right") - 1
+    cnt = np.diff(Pc.indptr)
+    has = cnt > 0
+    mid = Pc.indptr[:-1] + cnt // 2
+    rows_mid = np.zeros(nc, dtype=np.int64)
+    rows_mid[has] = Pc.indices[mid[has]]
+    owner = np.searchsorted(fine_off, rows_mid, side="right") - 1
     owner[~has] = 0
     order = np.lexsort((np.arange(nc), owner)).astype(np.int64)
     counts = np.bincount(owner, minlength=nranks)
