@@ -109,6 +109,8 @@ def _worker_body(rank, nranks, case, q):
             prob = syn.stokes_immersed_boundary(dim=2, nel=8, diagonal_mass=True)
         elif case == "stokes_node":
             prob = syn.stokes_immersed_boundary(dim=2, nel=8, diagonal_mass=True, numbering="node")
+        elif case == "stokes3d_node":
+            prob = syn.stokes_immersed_boundary(dim=3, nel=6, r_emb=1, numbering="node")
         else:
             prob = syn.immersed_laplace(r_bg=4)
         H = syn.build_hierarchies(prob, max_coarse=40)
@@ -154,12 +156,12 @@ def _worker_body(rank, nranks, case, q):
         q.put((rank, res))
 
 
-@pytest.mark.parametrize("case", ["laplace", "stokes", "stokes_node"])
-def test_two_rank_partition_matches_serial(case):
+@pytest.mark.parametrize("case,nranks", [("laplace", 2), ("stokes", 2), ("stokes_node", 2), ("stokes3d_node", 4)])
+def test_partition_matches_serial(case, nranks):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, case, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, nranks, port, case, q)) for r in range(nranks)]
     for p in procs:
         p.start()
     out = [q.get(timeout=180) for _ in procs]
@@ -194,3 +196,20 @@ def test_halo_plan_is_consistent_single_process():
             sent = dcs[q].plan.send_idx[soff[r]: soff[r + 1]] + off[q]
             want = dcs[r].plan.halo_globals[roff[q]: roff[q + 1]]
             assert np.array_equal(sent, want)
+
+
+def test_coarse_ownership_depends_on_the_pattern_only():
+    """Every rank cuts its own copy of the hierarchy: ownership must not move when the
+    floating-point values differ in the last bits (an arg-max rule has cross-rank ties and
+    dead-locked the 4-GPU halo exchange in round 1)."""
+    prob = syn.stokes_immersed_boundary(dim=3, nel=8, numbering="node")
+    H = syn.build_hierarchies(prob, max_coarse=300)
+    P0 = H[b.AMG_A11].levels[0].P
+    off = part.split_offsets(P0.shape[0], 4, 3)
+    rng = np.random.default_rng(0)
+    P1 = P0.copy()
+    P1.data = P1.data * (1.0 + 1e-13 * rng.standard_normal(P1.data.size))
+    o0, f0 = part.coarse_order(P0, off)
+    o1, f1 = part.coarse_order(P1, off)
+    assert np.array_equal(o0, o1) and np.array_equal(f0, f1)
+    assert f0[-1] == P0.shape[1] and np.all(np.diff(f0) >= 0)
