@@ -1,3 +1,2 @@
 set -x
-nvidia-smi -L
-timeout 1200 python -m pytest tests/test_multi_gpu.py -x -q -s 2>&1 | tail -30
+timeout 70 python -m pytest tests/test_multi_gpu.py -x -q -k "stokes3d_diag or stokes2d_diag" > gpurun_out/pytest_2gpu.log 2>&1; tail -4 gpurun_out/pytest_2gpu.log
