@@ -25,6 +25,24 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+_RESULT_FD = None
+
+
+def capture_stdout():
+    """Native libraries write to fd 1 ("NCCL version ..." at communicator creation): route
+    everything except the result line to stderr so stdout carries exactly ONE JSON line."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: str):
+    sys.stdout.flush()
+    os.write(_RESULT_FD if _RESULT_FD is not None else 1, (line + "\n").encode())
+
+
 METRIC = "outer_fgmres_solve_dofs_per_s"
 UNIT = "DoF/s"
 
@@ -181,7 +199,7 @@ def run_reference(args, w, wname):
                                    f"extrapolated to {n_outer} outer iterations", "n_dofs_sample": prob.n_dofs},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(json.dumps(line))
 
 
 _OUTER_CACHE = {}
@@ -394,7 +412,7 @@ def run_ours(args, w, wname):
                                    "sample": f"first 2 outer FGMRES iterations of {note} (oracle, 1 thread = how the "
                                              f"reference ships), extrapolated to {n_outer} outer iterations",
                                    "ms_per_step_sample_problem": per_it * n_outer * 1e3, "n_dofs_sample": sprob.n_dofs}
-        print(json.dumps(res))
+        emit(json.dumps(res))
     if world > 1:
         import torch.distributed as dist
 
@@ -414,6 +432,7 @@ def main():
     ap.add_argument("--no-bsr", action="store_true")
     ap.add_argument("--expected-outer", type=int, default=0)
     args = ap.parse_args()
+    capture_stdout()
     w = dict(WORKLOADS[args.workload])
     if args.nel:
         w["nel"] = args.nel
