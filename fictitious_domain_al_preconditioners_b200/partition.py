@@ -60,6 +60,32 @@ def _node_complete(cols: np.ndarray, bs: int) -> np.ndarray:
     return (nodes[:, None] * bs + np.arange(bs, dtype=nodes.dtype)[None, :]).reshape(-1)
 
 
+_NEEDS_CACHE: dict = {}
+
+
+def clear_cache():
+    _NEEDS_CACHE.clear()
+
+
+def _halo_needs(A: sp.csr_matrix, row_off, col_off, col_bs: int):
+    """For every rank q: the sorted, node-complete list of columns its rows touch outside its
+    own column range.  Cached per matrix object so that cutting all ranks' shares on one
+    process (rank-0 setup) costs one pass instead of one per rank."""
+    key = (id(A), A.nnz, tuple(int(x) for x in row_off), tuple(int(x) for x in col_off), col_bs)
+    hit = _NEEDS_CACHE.get(key)
+    if hit is not None:
+        return hit
+    nranks = len(row_off) - 1
+    out = []
+    for q in range(nranks):
+        lo, hi = int(A.indptr[int(row_off[q])]), int(A.indptr[int(row_off[q + 1])])
+        cq = A.indices[lo:hi].astype(np.int64)
+        q0, q1 = int(col_off[q]), int(col_off[q + 1])
+        out.append(_node_complete(cq[(cq < q0) | (cq >= q1)], col_bs))
+    _NEEDS_CACHE[key] = out
+    return out
+
+
 def localize(A: sp.csr_matrix, row_off: np.ndarray, col_off: np.ndarray, rank: int, col_bs: int = 1) -> DistCsr:
     """Rows row_off[rank]:row_off[rank+1] of the (renumbered) global matrix with a halo plan
     over the column space partitioned by col_off.  col_bs > 1: the column space is
@@ -73,7 +99,8 @@ def localize(A: sp.csr_matrix, row_off: np.ndarray, col_off: np.ndarray, rank: i
     sub = A[int(row_off[rank]): int(row_off[rank + 1])].tocsr()
     cols = sub.indices.astype(np.int64)
     owned = (cols >= c0) & (cols < c1)
-    halo_globals = _node_complete(cols[~owned], col_bs)
+    needs = _halo_needs(A, row_off, col_off, col_bs)  # per rank: node-complete non-owned columns
+    halo_globals = needs[rank]
     newcol = np.empty_like(cols)
     newcol[owned] = cols[owned] - c0
     newcol[~owned] = (c1 - c0) + np.searchsorted(halo_globals, cols[~owned])
@@ -86,10 +113,7 @@ def localize(A: sp.csr_matrix, row_off: np.ndarray, col_off: np.ndarray, rank: i
         if q == rank:
             send_lists.append(np.empty(0, dtype=np.int64))
             continue
-        subq = A[int(row_off[q]): int(row_off[q + 1])]
-        cq = subq.indices.astype(np.int64)
-        q0, q1 = int(col_off[q]), int(col_off[q + 1])
-        cq = _node_complete(cq[(cq < q0) | (cq >= q1)], col_bs)
+        cq = needs[q]
         mine = cq[(cq >= c0) & (cq < c1)]
         send_lists.append(mine - c0)
     send_counts = np.array([s.size for s in send_lists], dtype=np.int32)
@@ -176,6 +200,9 @@ class LocalProblem:
     sizes_global: tuple = ()
     sizes_local: tuple = ()
     block_size: int = 1
+    rhs_local: np.ndarray | None = None  # filled by share_local_problems
+    augment_rhs: bool = False
+    meta: dict = field(default_factory=dict)
 
     # ---- vectors ---------------------------------------------------------------------
     def scatter(self, x_global: np.ndarray) -> np.ndarray:
@@ -312,3 +339,52 @@ def setup_local_context(ctx, lp: LocalProblem, uid: bytes = bytes(128)):
             ctx.set_amg(which, H)
     ctx.finalize()
     return ctx
+
+
+def distribute_all(prob, hierarchies: dict, nranks: int) -> list:
+    """Every rank's LocalProblem, cut on one process."""
+    out = [distribute_problem(prob, hierarchies, r, nranks) for r in range(nranks)]
+    clear_cache()
+    return out
+
+
+def share_local_problems(build_fn, rank: int, nranks: int, group=None):
+    """Setup on rank 0 only: ``build_fn()`` -> (problem, hierarchies, meta dict) runs once, the
+    ranks' shares travel through pickle files in shared memory.  One copy of the global
+    problem in host memory instead of one per rank, and every rank's plan comes from the SAME
+    hierarchy (nothing to disagree about).  Returns this rank's LocalProblem with ``rhs_local``,
+    ``augment_rhs`` and ``meta`` filled in."""
+    import os
+    import pickle
+    import shutil
+    import tempfile
+
+    import torch.distributed as dist
+
+    box = [None]
+    if rank == 0:
+        prob, H, meta = build_fn()
+        base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+        d = tempfile.mkdtemp(prefix="fdal_lp_", dir=base)
+        for r in range(nranks):
+            lp = distribute_problem(prob, H, r, nranks)
+            lp.rhs_local = lp.scatter(prob.rhs)
+            lp.augment_rhs = bool(prob.augment_rhs)
+            lp.meta = dict(meta)
+            with open(os.path.join(d, f"lp_{r}.pkl"), "wb") as f:
+                pickle.dump(lp, f, protocol=5)
+            del lp
+        clear_cache()
+        del prob, H
+        box[0] = d
+    if nranks > 1:
+        dist.broadcast_object_list(box, src=0, group=group)
+    d = box[0]
+    with open(os.path.join(d, f"lp_{rank}.pkl"), "rb") as f:
+        lp = pickle.load(f)
+    os.remove(os.path.join(d, f"lp_{rank}.pkl"))
+    if nranks > 1:
+        dist.barrier(group=group)
+    if rank == 0:
+        shutil.rmtree(d, ignore_errors=True)
+    return lp

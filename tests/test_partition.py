@@ -213,3 +213,49 @@ def test_coarse_ownership_depends_on_the_pattern_only():
     o1, f1 = part.coarse_order(P1, off)
     assert np.array_equal(o0, o1) and np.array_equal(f0, f1)
     assert f0[-1] == P0.shape[1] and np.all(np.diff(f0) >= 0)
+
+
+def _share_worker(rank, nranks, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=nranks)
+    try:
+        built = []
+
+        def build():
+            built.append(rank)
+            prob = syn.stokes_immersed_boundary(dim=2, nel=8, diagonal_mass=True, numbering="node")
+            return prob, syn.build_hierarchies(prob, max_coarse=40), {"n_dofs": prob.n_dofs}
+
+        lp = part.share_local_problems(build, rank, nranks)
+        prob = syn.stokes_immersed_boundary(dim=2, nel=8, diagonal_mass=True, numbering="node")
+        ref = part.distribute_problem(prob, syn.build_hierarchies(prob, max_coarse=40), rank, nranks)
+        ok = built == ([0] if rank == 0 else [])  # only rank 0 ran the setup
+        ok &= lp.rank == rank and lp.meta["n_dofs"] == prob.n_dofs and lp.augment_rhs
+        ok &= np.array_equal(lp.rhs_local, ref.scatter(prob.rhs))
+        for mid in ref.mats:
+            ok &= (lp.mats[mid].local != ref.mats[mid].local).nnz == 0
+            if ref.mats[mid].plan is not None:
+                ok &= np.array_equal(lp.mats[mid].plan.send_idx, ref.mats[mid].plan.send_idx)
+        ok &= len(lp.amg[b.AMG_A11].levels) == len(ref.amg[b.AMG_A11].levels)
+        q.put((rank, bool(ok)))
+    except Exception:
+        import traceback
+
+        q.put((rank, traceback.format_exc()[-1500:]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_rank0_setup_is_shared_with_the_other_ranks():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_share_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, ok in out:
+        assert ok is True, ok
