@@ -79,3 +79,69 @@ def test_own_arm_control_flow_emits_the_contract_keys(monkeypatch, capfd):
     assert d["roofline"]["bound"] == "hbm" and d["roofline"]["unit"] == "GB/s" and "frac" in d["roofline"]
     assert d["e2e"]["h2d_bytes_per_step"] == 16 * d["config"]["n_dofs"]
     assert d["gpu_launches"] == 2 * 1234 and d["dtype"] == "f64" and d["vs_baseline"] is None
+
+
+def _two_rank_worker(rank, port, q):
+    import unittest.mock as mock
+
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+
+    import bench
+    import fictitious_domain_al_preconditioners_b200 as pkg
+    from fictitious_domain_al_preconditioners_b200 import partition as part
+
+    real_init = dist.init_process_group
+    real_zeros = torch.zeros
+    real_tensor = torch.tensor
+    lines = []
+    try:
+        with mock.patch.object(pkg, "ALContext", _FakeCtx), \
+                mock.patch.object(part, "setup_local_context", lambda ctx, lp, uid=bytes(128): ctx), \
+                mock.patch.object(torch.cuda, "set_device", lambda *a, **k: None), \
+                mock.patch.object(torch.cuda, "synchronize", lambda *a, **k: None), \
+                mock.patch.object(torch.Tensor, "cuda", lambda self, *a, **k: self), \
+                mock.patch.object(torch.Tensor, "pin_memory", lambda self, *a, **k: self), \
+                mock.patch.object(torch, "zeros", lambda *a, **k: real_zeros(*a, **{kk: v for kk, v in k.items() if kk != "device"})), \
+                mock.patch.object(torch, "tensor", lambda *a, **k: real_tensor(*a, **{kk: v for kk, v in k.items() if kk != "device"})), \
+                mock.patch.object(dist, "init_process_group", lambda backend, **k: real_init("gloo")), \
+                mock.patch.object(bench, "emit", lambda s: lines.append(s)), \
+                mock.patch.object(bench.ClockSampler, "start", lambda self: None), \
+                mock.patch.object(bench.ClockSampler, "stop", lambda self: {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}):
+            args = argparse.Namespace(gpus=2, steps=1, warmup=1, impl="ours", workload="tiny", nel=0, no_cpu=True,
+                                      no_graphs=False, no_bsr=False, expected_outer=0)
+            bench.run_ours(args, dict(bench.WORKLOADS["tiny"]), "tiny")
+        q.put((rank, lines))
+    except Exception:
+        import traceback
+
+        q.put((rank, "ERR " + traceback.format_exc()[-2500:]))
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="dry run is for GPU-less boxes")
+def test_two_rank_control_flow_rank0_setup_and_single_json_line():
+    import socket
+
+    import torch.multiprocessing as mp
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_two_rank_worker, args=(r, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = dict(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert not isinstance(out[0], str), out[0]
+    assert not isinstance(out[1], str), out[1]
+    assert len(out[0]) == 1 and len(out[1]) == 0  # rank 0 alone prints
+    d = json.loads(out[0][0])
+    assert d["n_gpus"] == 2 and d["scaling"] == "weak" and "weak-scaled x2" in d["config"]["description"]
+    assert d["config"]["n_dofs"] > 9605  # the global job grew with the rank count
+    assert d["config"]["setup"].startswith("rank 0 builds")
