@@ -275,8 +275,13 @@ def run_ours(args, w, wname):
 
         # setup on rank 0 only (one copy of the global problem in host memory, one hierarchy
         # for every rank's halo plan); the shares travel through shared-memory files
+        from fictitious_domain_al_preconditioners_b200 import amg_setup
+
         gloo = dist.new_group(backend="gloo")
+        ncpu = os.cpu_count() or 1
+        amg_setup.set_host_threads(ncpu if rank == 0 else 1)  # rank 0 sets up with the whole box
         lp = part.share_local_problems(build, rank, world, gloo)
+        amg_setup.set_host_threads(max(1, ncpu // world))  # then every rank gets its share
     else:
         prob, H, meta = build()
         lp = part.distribute_problem(prob, H, 0, 1)

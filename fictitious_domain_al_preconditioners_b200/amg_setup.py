@@ -68,6 +68,14 @@ import time
 _VERBOSE = bool(os.environ.get("FDAL_VERBOSE_SETUP"))
 
 
+def set_host_threads(n: int):
+    """Thread budget of the OpenMP setup helpers (SpGEMM here, BSR conversion in libfdal)."""
+    lib = _host()
+    lib.fdal_host_set_num_threads.argtypes = [C.c_int]
+    lib.fdal_host_set_num_threads.restype = None
+    lib.fdal_host_set_num_threads(int(n))
+
+
 def _log(msg):
     if _VERBOSE:
         sys.stderr.write(f"[setup] {msg}\n")

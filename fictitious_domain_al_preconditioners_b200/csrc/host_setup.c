@@ -141,3 +141,21 @@ void fdal_host_spgemm_numeric(int64_t n_rows, int64_t n_cols_b, const int64_t *A
     free(acc);
   }
 }
+
+/* thread budget of the OpenMP helpers (bench: rank 0 uses the whole box during the shared
+ * setup, every rank its share afterwards); the CUDA library's BSR conversion uses the same
+ * libgomp runtime */
+void fdal_host_set_num_threads(int n) {
+#ifdef _OPENMP
+  omp_set_num_threads(n < 1 ? 1 : n);
+#else
+  (void)n;
+#endif
+}
+int fdal_host_get_max_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
