@@ -363,22 +363,31 @@ def share_local_problems(build_fn, rank: int, nranks: int, group=None):
 
     box = [None]
     if rank == 0:
-        prob, H, meta = build_fn()
-        base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
-        d = tempfile.mkdtemp(prefix="fdal_lp_", dir=base)
-        for r in range(nranks):
-            lp = distribute_problem(prob, H, r, nranks)
-            lp.rhs_local = lp.scatter(prob.rhs)
-            lp.augment_rhs = bool(prob.augment_rhs)
-            lp.meta = dict(meta)
-            with open(os.path.join(d, f"lp_{r}.pkl"), "wb") as f:
-                pickle.dump(lp, f, protocol=5)
-            del lp
-        clear_cache()
-        del prob, H
-        box[0] = d
+        try:
+            prob, H, meta = build_fn()
+            # shared memory when it is large enough (container /dev/shm is often 64 MB), else /tmp
+            cands = [p_ for p_ in ("/dev/shm", tempfile.gettempdir()) if os.path.isdir(p_) and os.access(p_, os.W_OK)]
+            base = max(cands, key=lambda p_: shutil.disk_usage(p_).free) if cands else None
+            d = tempfile.mkdtemp(prefix="fdal_lp_", dir=base)
+            for r in range(nranks):
+                lp = distribute_problem(prob, H, r, nranks)
+                lp.rhs_local = lp.scatter(prob.rhs)
+                lp.augment_rhs = bool(prob.augment_rhs)
+                lp.meta = dict(meta)
+                with open(os.path.join(d, f"lp_{r}.pkl"), "wb") as f:
+                    pickle.dump(lp, f, protocol=5)
+                del lp
+            clear_cache()
+            del prob, H
+            box[0] = d
+        except Exception as e:  # tell the other ranks instead of leaving them in the broadcast
+            import traceback
+
+            box[0] = ("ERR", f"{type(e).__name__}: {e}\n{traceback.format_exc()[-1500:]}")
     if nranks > 1:
         dist.broadcast_object_list(box, src=0, group=group)
+    if isinstance(box[0], tuple):
+        raise RuntimeError(f"setup on rank 0 failed: {box[0][1]}")
     d = box[0]
     with open(os.path.join(d, f"lp_{rank}.pkl"), "rb") as f:
         lp = pickle.load(f)
