@@ -250,6 +250,17 @@ def run_ours(args, w, wname):
     if world > 1:
         import torch.distributed as dist
 
+        # a rank that fails leaves the others inside an NCCL call for ever: bound the damage
+        limit = float(os.environ.get("FDAL_BENCH_WATCHDOG_S", "1500"))
+
+        def _bail():
+            sys.stderr.write(f"[bench] rank {rank}: watchdog fired after {limit:.0f} s, aborting\n")
+            sys.stderr.flush()
+            os._exit(3)
+
+        wd = threading.Timer(limit, _bail)
+        wd.daemon = True
+        wd.start()
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
