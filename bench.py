@@ -160,6 +160,19 @@ def bounded_cpu_problem(w, prob, H):
     return sprob, sH, f"the same parameter file at nel={w2['nel']} ({sprob.n_dofs} DoFs)"
 
 
+def estimate_dofs(w):
+    """DoFs of a Stokes workload without building it (the reference arm only needs the count)."""
+    if w.get("kind") != "stokes":
+        return None
+    dim, nel = w["dim"], w["nel"]
+    if dim == 2:
+        m = 2 * (2 ** int(round(np.log2(nel))) + 1)
+    else:
+        k = max(1, int(round(np.log2(nel))) - 3)
+        m = 3 * (6 * 4**k + 2)
+    return dim * (2 * nel + 1) ** dim + (nel + 1) ** dim + m
+
+
 def run_reference(args, w, wname):
     """--impl reference: the reference's CPU path.  The reference binary cannot be
     built here (deal.II / Trilinos / UMFPACK absent), so this times the oracle port
@@ -176,9 +189,18 @@ def run_reference(args, w, wname):
         w = dict(w)
         w["nel"] = int(round(w["nel"] * world ** (1.0 / w["dim"]) / 2.0)) * 2
         w["label"] = w["label"].rsplit("nel=", 1)[0] + f"nel={w['nel']} (weak-scaled x{world})"
-    prob, H = build_problem(w)
-    n_full = prob.n_dofs
-    prob, H, note = bounded_cpu_problem(w, prob, H)
+    n_est = estimate_dofs(w)
+    if n_est is not None and n_est > CPU_SAMPLE_MAX_DOFS:
+        # do not assemble the big problem just to count its unknowns
+        w2 = dict(w)
+        w2["nel"] = max(8, int(w["nel"] * (1.0e6 / n_est) ** (1.0 / w["dim"]) / 2) * 2)
+        prob, H = build_problem(w2)
+        n_full = n_est
+        note = f"the same parameter file at nel={w2['nel']} ({prob.n_dofs} DoFs)"
+    else:
+        prob, H = build_problem(w)
+        n_full = prob.n_dofs
+        prob, H, note = bounded_cpu_problem(w, prob, H)
     sample_outer = 2
     vals = []
     for i in range(args.warmup + args.steps):
