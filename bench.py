@@ -446,6 +446,7 @@ def run_ours(args, w, wname):
             "roofline": {"bound": "hbm", "kernel": "fused Chebyshev step on the finest AMG level (k_bsr_spmv<B,TPR,EpiCheb> / k_spmv<TPR,EpiCheb>)",
                          "achieved": dom.get("GBps"), "peak": peak, "unit": "GB/s",
                          "frac": dom.get("frac"), "traffic": traffic, "algorithmic_bytes": dom.get("alg_bytes"),
+                         "frac_of_nominal_8000GBs": (dom.get("GBps") / 8000.0) if dom.get("GBps") else None,
                          "peak_source": peak_src},
             "kernels": kern,
         }
