@@ -69,3 +69,23 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".c", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "fdal_oracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, f
+
+
+def test_header_is_plain_c_and_a_c_client_links(tmp_path):
+    """include/fdal.h compiles as C99 and as C++17, and a C program (examples/c_abi_smoke.c) links
+    against libfdal.so with nothing but the C ABI; on a box without a GPU it reports
+    FDAL_ERR_CUDA and exits 0, on a GPU box it runs a tiny solve."""
+    import subprocess
+
+    inc = os.path.join(ROOT, "include")
+    hdr = os.path.join(inc, "fdal.h")
+    subprocess.run(["/usr/bin/gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", hdr], check=True)
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", hdr], check=True)
+    lib = build.build()
+    exe = str(tmp_path / "c_abi_smoke")
+    libdir = os.path.dirname(lib)
+    subprocess.run(["/usr/bin/gcc", "-std=c99", "-I", inc, os.path.join(ROOT, "examples", "c_abi_smoke.c"), "-L", libdir,
+                    "-lfdal", f"-Wl,-rpath,{libdir}", "-o", exe], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.startswith("fdal ")
