@@ -255,69 +255,97 @@ def _perm(A, row_order, col_order):
     return A
 
 
-def distribute_hierarchy(H, order0, off0, rank, nranks, bs: int = 1) -> LocalHierarchy:
-    levels = []
-    order_f, off_f = order0, off0
-    nl = len(H.levels)
-    Aperm = _perm(H.levels[0].A, order_f, order_f)
-    for l in range(nl - 1):
-        L = H.levels[l]
-        order_c, off_c = coarse_order(_perm(L.P, order_f, None), off_f)
-        Pp = _perm(L.P, order_f, order_c)
-        Rp = _perm(L.R if L.R is not None else L.P.T, order_c, order_f)
-        lbs = bs if l == 0 else 1
-        levels.append(LocalLevel(
-            A=localize(Aperm, off_f, off_f, rank, lbs),
-            P=localize(Pp, off_f, off_c, rank),
-            R=localize(Rp, off_c, off_f, rank, lbs),
-            inv_diag=None if L.inv_diag is None else
-            (L.inv_diag if order_f is None else L.inv_diag[order_f])[off_f[rank]: off_f[rank + 1]],
-            lambda_max=L.lambda_max,
-        ))
-        order_f, off_f = order_c, off_c
-        Aperm = _perm(H.levels[l + 1].A, order_f, order_f)
-    return LocalHierarchy(levels=levels, coarse_A=Aperm, coarse_off=off_f, cheb_degree=H.cheb_degree,
-                          eig_ratio=H.eig_ratio)
+class Distributor:
+    """Cuts a Problem (+ AMG hierarchies) for `nranks` ranks.  Everything that does not depend
+    on the rank — renumbered matrices, transposes, coarse ownership — is computed once, so
+    cutting all ranks' shares on one process (rank-0 setup) is one pass plus row slicing."""
+
+    def __init__(self, prob, hierarchies: dict, nranks: int):
+        self.prob, self.nranks = prob, nranks
+        kind = prob.config.kind
+        n, m = prob.Ct.shape
+        self.order0, self.bs = block0_order(prob)
+        self.off0 = split_offsets(n, nranks, self.bs)
+        self.A = _perm(prob.A, self.order0, self.order0)
+        self.Ct = _perm(prob.Ct, self.order0, None)
+        self.C = sp.csr_matrix(self.Ct.T).tocsc()  # column slices per rank
+        self.stokes = kind in (b.KIND_STOKES, b.KIND_STOKES_DIAG_MINRES)
+        if self.stokes:
+            n_p = prob.Bt.shape[1]
+            self.order1 = np.arange(n_p, dtype=np.int64)
+            self.off1 = split_offsets(n_p, nranks)
+            self.Bt = _perm(prob.Bt, self.order0, self.order1)
+            self.B = sp.csr_matrix(self.Bt.T)
+            self.Mp = _perm(prob.Mp, self.order1, self.order1)
+        # hierarchy of the background block: renumber every level once
+        self.hier = {}
+        for which, H in hierarchies.items():
+            if which != b.AMG_A11:
+                self.hier[which] = H  # immersed block: replicated
+                continue
+            levels = []
+            order_f, off_f = self.order0, self.off0
+            Aperm = _perm(H.levels[0].A, order_f, order_f)
+            for l in range(len(H.levels) - 1):
+                L = H.levels[l]
+                order_c, off_c = coarse_order(_perm(L.P, order_f, None), off_f)
+                Pp = _perm(L.P, order_f, order_c)
+                Rp = _perm(L.R if L.R is not None else L.P.T, order_c, order_f)
+                invd = None if L.inv_diag is None else (L.inv_diag if order_f is None else L.inv_diag[order_f])
+                levels.append(dict(A=Aperm, P=Pp, R=Rp, inv_diag=invd, lambda_max=L.lambda_max, off_f=off_f, off_c=off_c,
+                                   bs=self.bs if l == 0 else 1))
+                order_f, off_f = order_c, off_c
+                Aperm = _perm(H.levels[l + 1].A, order_f, order_f)
+            self.hier[which] = dict(levels=levels, coarse_A=Aperm, coarse_off=off_f, cheb_degree=H.cheb_degree,
+                                    eig_ratio=H.eig_ratio)
+
+    def local(self, rank: int) -> LocalProblem:
+        prob, nranks, off0, bs = self.prob, self.nranks, self.off0, self.bs
+        kind = prob.config.kind
+        m = prob.Ct.shape[1]
+        lp = LocalProblem(rank=rank, nranks=nranks, config=prob.config, order0=self.order0, off0=off0,
+                          sizes_global=prob.sizes, winv_diag=prob.winv_diag)
+        lp.block_size = bs
+        r0, r1 = int(off0[rank]), int(off0[rank + 1])
+        lp.mats[b.MAT_A] = localize(self.A, off0, off0, rank, bs)
+        lp.mats[b.MAT_CT] = DistCsr(self.Ct[r0:r1].tocsr(), None)
+        lp.mats[b.MAT_C] = DistCsr(self.C[:, r0:r1].tocsr(), None)
+        lp.mats[b.MAT_M] = DistCsr(prob.M.tocsr(), None)
+        n_loc = r1 - r0
+        if self.stokes:
+            off1 = self.off1
+            lp.order1, lp.off1 = self.order1, off1
+            lp.mats[b.MAT_BT] = localize(self.Bt, off0, off1, rank)
+            lp.mats[b.MAT_B] = localize(self.B, off1, off0, rank, bs)
+            lp.mats[b.MAT_MP] = localize(self.Mp, off1, off1, rank)
+            lp.sizes_local = (n_loc, int(off1[rank + 1] - off1[rank]), m)
+        elif kind == b.KIND_LAPLACE:
+            lp.sizes_local = (n_loc, m)
+        else:
+            lp.mats[b.MAT_A2] = DistCsr(prob.A2.tocsr(), None)
+            lp.sizes_local = (n_loc, m, m)
+        for which, Hd in self.hier.items():
+            if which != b.AMG_A11:
+                lp.amg[which] = Hd
+                continue
+            levels = []
+            for L in Hd["levels"]:
+                off_f, off_c = L["off_f"], L["off_c"]
+                levels.append(LocalLevel(
+                    A=localize(L["A"], off_f, off_f, rank, L["bs"]),
+                    P=localize(L["P"], off_f, off_c, rank),
+                    R=localize(L["R"], off_c, off_f, rank, L["bs"]),
+                    inv_diag=None if L["inv_diag"] is None else L["inv_diag"][off_f[rank]: off_f[rank + 1]],
+                    lambda_max=L["lambda_max"]))
+            lp.amg[which] = LocalHierarchy(levels=levels, coarse_A=Hd["coarse_A"], coarse_off=Hd["coarse_off"],
+                                           cheb_degree=Hd["cheb_degree"], eig_ratio=Hd["eig_ratio"])
+        return lp
 
 
 def distribute_problem(prob, hierarchies: dict, rank: int, nranks: int) -> LocalProblem:
     """This rank's share of a Problem (+ AMG hierarchies)."""
-    kind = prob.config.kind
-    n, m = prob.Ct.shape
-    order0, bs = block0_order(prob)
-    off0 = split_offsets(n, nranks, bs)
-    lp = LocalProblem(rank=rank, nranks=nranks, config=prob.config, order0=order0, off0=off0,
-                      sizes_global=prob.sizes, winv_diag=prob.winv_diag)
-    rep_off = np.array([0] + [m] * nranks, dtype=np.int64)  # unused: replicated spaces have no plan
-    A = _perm(prob.A, order0, order0)
-    lp.block_size = bs
-    lp.mats[b.MAT_A] = localize(A, off0, off0, rank, bs)
-    Ct = _perm(prob.Ct, order0, None)
-    lp.mats[b.MAT_CT] = DistCsr(Ct[off0[rank]: off0[rank + 1]].tocsr(), None)
-    C = sp.csr_matrix(Ct.T)
-    lp.mats[b.MAT_C] = DistCsr(C[:, off0[rank]: off0[rank + 1]].tocsr(), None)
-    lp.mats[b.MAT_M] = DistCsr(prob.M.tocsr(), None)
-    n_loc = int(off0[rank + 1] - off0[rank])
-    if kind in (b.KIND_STOKES, b.KIND_STOKES_DIAG_MINRES):
-        n_p = prob.Bt.shape[1]
-        order1 = np.arange(n_p, dtype=np.int64)
-        off1 = split_offsets(n_p, nranks)
-        lp.order1, lp.off1 = order1, off1
-        Bt = _perm(prob.Bt, order0, order1)
-        lp.mats[b.MAT_BT] = localize(Bt, off0, off1, rank)
-        lp.mats[b.MAT_B] = localize(sp.csr_matrix(Bt.T), off1, off0, rank, bs)
-        lp.mats[b.MAT_MP] = localize(_perm(prob.Mp, order1, order1), off1, off1, rank)
-        lp.sizes_local = (n_loc, int(off1[rank + 1] - off1[rank]), m)
-    elif kind == b.KIND_LAPLACE:
-        lp.sizes_local = (n_loc, m)
-    else:
-        lp.mats[b.MAT_A2] = DistCsr(prob.A2.tocsr(), None)
-        lp.sizes_local = (n_loc, m, m)
-    for which, H in hierarchies.items():
-        if which == b.AMG_A11:
-            lp.amg[which] = distribute_hierarchy(H, order0, off0, rank, nranks, bs)
-        else:  # immersed block: replicated hierarchy
-            lp.amg[which] = H
+    lp = Distributor(prob, hierarchies, nranks).local(rank)
+    clear_cache()
     return lp
 
 
@@ -343,7 +371,8 @@ def setup_local_context(ctx, lp: LocalProblem, uid: bytes = bytes(128)):
 
 def distribute_all(prob, hierarchies: dict, nranks: int) -> list:
     """Every rank's LocalProblem, cut on one process."""
-    out = [distribute_problem(prob, hierarchies, r, nranks) for r in range(nranks)]
+    D = Distributor(prob, hierarchies, nranks)
+    out = [D.local(r) for r in range(nranks)]
     clear_cache()
     return out
 
@@ -369,8 +398,9 @@ def share_local_problems(build_fn, rank: int, nranks: int, group=None):
             cands = [p_ for p_ in ("/dev/shm", tempfile.gettempdir()) if os.path.isdir(p_) and os.access(p_, os.W_OK)]
             base = max(cands, key=lambda p_: shutil.disk_usage(p_).free) if cands else None
             d = tempfile.mkdtemp(prefix="fdal_lp_", dir=base)
+            D = Distributor(prob, H, nranks)
             for r in range(nranks):
-                lp = distribute_problem(prob, H, r, nranks)
+                lp = D.local(r)
                 lp.rhs_local = lp.scatter(prob.rhs)
                 lp.augment_rhs = bool(prob.augment_rhs)
                 lp.meta = dict(meta)
@@ -378,7 +408,7 @@ def share_local_problems(build_fn, rank: int, nranks: int, group=None):
                     pickle.dump(lp, f, protocol=5)
                 del lp
             clear_cache()
-            del prob, H
+            del prob, H, D
             box[0] = d
         except Exception as e:  # tell the other ranks instead of leaving them in the broadcast
             import traceback
