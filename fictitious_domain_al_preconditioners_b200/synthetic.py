@@ -564,6 +564,7 @@ def stokes_immersed_boundary(
     build_amg_matrix: bool = True,
     fast: bool | None = None,
     numbering: str = "component",
+    grad_div_stabilization: bool = True,
 ) -> Problem:
     """3x3 system of stokes_immersed_boundary with ``Solver = IBStokesAL``
     (parameters_stokes.prm in 2-D, parameters_stokes_3d.prm in 3-D;
@@ -573,6 +574,13 @@ def stokes_immersed_boundary(
     h = 1.0 / nel
     if diagonal_mass is None:
         diagonal_mass = dim == 3  # parameters_stokes.prm:21 false, parameters_stokes_3d.prm:18 true
+    gamma_gd_operator = gamma_grad_div
+    if not grad_div_stabilization:
+        # "Grad-div stabilization = false": the (div,div) term is not assembled into A; the operator
+        # carries gamma_gd Bt Mp^-1 B instead and the inner CG runs unpreconditioned
+        # (stokes_immersed_boundary.cc:992-995, 1046-1051)
+        gamma_grad_div = 0.0
+        build_amg_matrix = False
     K2, M2 = fe1d(nel, h, 2, 2, 1, 1), fe1d(nel, h, 2, 2)
     D10 = fe1d(nel, h, 2, 2, 1, 0)
     F = fe1d(nel, h, 1, 2, 0, 0)
@@ -666,7 +674,9 @@ def stokes_immersed_boundary(
         kind=b.KIND_STOKES_DIAG_MINRES if diag_minres else b.KIND_STOKES,
         restart=30,
         gamma=gamma,
-        gamma_grad_div=gamma_grad_div,
+        gamma_grad_div=gamma_gd_operator,
+        grad_div_in_operator=not grad_div_stabilization,
+        inner_prec=b.PREC_AMG if grad_div_stabilization else b.PREC_IDENTITY,
         inner=SolverControl(100, 1e-2),  # ALControl: Max steps 100, tol_AL 1e-2
         outer=ReductionControl(1000, 1e-8, 1e-12),
         mass=SolverControl(100, 1e-6),  # stokes_immersed_boundary.cc:934

@@ -29,11 +29,21 @@ CASES = {
 }
 
 
+# cases whose CUDA path has not been run on a GPU yet (round 1 ran out of GPU budget): they are
+# full members of the CPU/oracle suites and non-strict xfail members of the GPU suite
+EXTRA_CASES = {
+    # "Grad-div stabilization = false": Aug += gamma_gd Bt Mp^-1 B, unpreconditioned inner CG
+    # (stokes_immersed_boundary.cc:992-995, 1046-1051)
+    "stokes2d_nogd": (syn.stokes_immersed_boundary, dict(dim=2, nel=8, grad_div_stabilization=False, diagonal_mass=True)),
+    "stokes2d_nogd_exact": (syn.stokes_immersed_boundary, dict(dim=2, nel=8, grad_div_stabilization=False)),
+}
+
+
 @functools.lru_cache(maxsize=None)
 def get(name):
-    fac, kw = CASES[name]
+    fac, kw = (CASES.get(name) or EXTRA_CASES[name])
     prob = fac(**kw)
-    H = syn.build_hierarchies(prob, max_coarse=300)  # >= 3 levels at these sizes
+    H = syn.build_hierarchies(prob, max_coarse=300) if prob.amg_matrix else {}  # >= 3 levels at these sizes
     return prob, H
 
 

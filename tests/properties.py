@@ -8,7 +8,7 @@ from fictitious_domain_al_preconditioners_b200 import _binding as b
 from . import problems as P
 
 
-def check_properties(ctx, prob, scatter=lambda v: v, gather=lambda v: v, tol=1e-11):
+def check_properties(ctx, prob, scatter=lambda v: v, gather=lambda v: v, tol=1e-11, with_amg=True, op_noise=0.0):
     """ctx: a finalized ALContext / OracleContext for `prob` (vectors pass through scatter/gather
     when the context works in a renumbered space).  Returns the solve info."""
     n0 = prob.sizes[0]
@@ -22,9 +22,10 @@ def check_properties(ctx, prob, scatter=lambda v: v, gather=lambda v: v, tol=1e-
     assert abs(yl @ Ax - xl @ Ay) <= tol * nrm(yl) * nrm(Ax)
     assert P.relerr(ctx.apply_aug(2.0 * xl - 3.0 * yl), 2.0 * Ax - 3.0 * Ay) < tol
     # (b) one V-cycle is a symmetric positive definite linear operator
-    Bx, By = ctx.apply_amg(xl), ctx.apply_amg(yl)
-    assert abs(yl @ Bx - xl @ By) <= tol * nrm(yl) * nrm(Bx)
-    assert xl @ Bx > 0 and yl @ By > 0
+    if with_amg:
+        Bx, By = ctx.apply_amg(xl), ctx.apply_amg(yl)
+        assert abs(yl @ Bx - xl @ By) <= tol * nrm(yl) * nrm(Bx)
+        assert xl @ Bx > 0 and yl @ By > 0
     # (c) the block system operator is symmetric for the 2x2 / Stokes systems
     if prob.config.kind in (b.KIND_LAPLACE, b.KIND_STOKES, b.KIND_STOKES_DIAG_MINRES):
         X, Y = scatter(P.rand(N, 33)), scatter(P.rand(N, 34))
@@ -46,7 +47,8 @@ def check_properties(ctx, prob, scatter=lambda v: v, gather=lambda v: v, tol=1e-
     assert info.status == 0
     true_res = np.linalg.norm(ctx.apply_system(sol) - rhs)
     oc = prob.config.outer
-    assert true_res <= 10.0 * max(oc.tol, oc.reduce * info.initial_residual)
+    # op_noise: level at which the operator itself is reproducible (nested inexact solves)
+    assert true_res <= 10.0 * max(oc.tol, oc.reduce * info.initial_residual, op_noise)
     h = info.history()
     assert h[-1] <= h[0] and info.outer_iterations == len(h) - 1
     assert info.inner_solves >= info.outer_iterations
@@ -55,5 +57,5 @@ def check_properties(ctx, prob, scatter=lambda v: v, gather=lambda v: v, tol=1e-
         full = gather(sol)
         n, m = prob.Ct.shape
         g = prob.rhs[-m:]
-        assert np.linalg.norm(prob.Ct.T @ full[:n] - g) <= 10.0 * max(oc.tol, oc.reduce * info.initial_residual)
+        assert np.linalg.norm(prob.Ct.T @ full[:n] - g) <= 10.0 * max(oc.tol, oc.reduce * info.initial_residual, op_noise)
     return info

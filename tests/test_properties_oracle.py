@@ -7,9 +7,13 @@ from . import problems as P
 from .properties import check_properties
 
 
-@pytest.mark.parametrize("name", ["laplace_diag", "stokes2d_diag", "stokes2d_exact", "stokes3d_node", "elliptic_modified_diag"])
+@pytest.mark.parametrize("name", ["laplace_diag", "stokes2d_diag", "stokes2d_exact", "stokes3d_node", "elliptic_modified_diag",
+                                  "stokes2d_nogd", "stokes2d_nogd_exact"])
 def test_properties_hold_for_the_oracle(name, oracle_mod):
     prob, H = P.get(name)
     ora = syn.setup_context(oracle_mod.OracleContext(prob.config), prob, H, oracle=True)
-    info = check_properties(ora, prob)
+    # the no-grad-div operator nests an INEXACT pressure-mass CG (abs tol 1e-6 on a matrix of size ~h^2, times
+    # gamma_gd): it is linear / symmetric only to ~1e-5 and FGMRES' residual estimate drifts from the true residual
+    tol = 1e-4 if name == "stokes2d_nogd" else 1e-11
+    info = check_properties(ora, prob, with_amg=bool(H), tol=tol, op_noise=5e-2 if name == "stokes2d_nogd" else 0.0)
     assert info.outer_iterations > 0
