@@ -204,18 +204,3 @@ def test_reference_style_operator_api(name, oracle_mod):
     xo, io = ora.solve(rhs.data)
     assert abs(info.outer_iterations - io.outer_iterations) <= 1
 
-
-@pytest.mark.xfail(strict=False, reason="CUDA path of the no-grad-div Stokes variant was not run on a GPU in round 1")
-@pytest.mark.parametrize("name", list(P.EXTRA_CASES))
-def test_extra_cases_not_yet_run_on_gpu(name, oracle_mod):
-    prob, gpu, ora = _pair(name, oracle_mod)
-    x = P.rand(prob.sizes[0], 3)
-    assert P.relerr(gpu.apply_aug(x), ora.apply_aug(x)) < 1e-10
-    X = P.rand(prob.n_dofs, 5)
-    assert P.relerr(gpu.apply_system(X), ora.apply_system(X)) < 1e-10
-    rhs = P.rhs_of(ora, prob)
-    xg, ig = gpu.solve(rhs)
-    xo, io = ora.solve(rhs)
-    assert abs(ig.outer_iterations - io.outer_iterations) <= 1
-    if ig.outer_iterations == io.outer_iterations:
-        assert P.relerr(xg, xo) < 1e-8
