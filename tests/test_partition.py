@@ -9,6 +9,7 @@ import numpy as np
 import pytest
 import torch
 import torch.distributed as dist
+import scipy.sparse as sp
 import torch.multiprocessing as mp
 
 from fictitious_domain_al_preconditioners_b200 import _binding as b
@@ -259,3 +260,33 @@ def test_rank0_setup_is_shared_with_the_other_ranks():
         p.join(timeout=60)
     for rank, ok in out:
         assert ok is True, ok
+
+
+def test_single_rank_share_is_the_renumbered_problem():
+    """nranks = 1 (the BSR path of bench.py and the GPU tests): the local problem is the global
+    one, renumbered node-major, with empty halo plans and an unchanged hierarchy."""
+    for numbering in ("node", "component"):
+        prob = syn.stokes_immersed_boundary(dim=2, nel=8, diagonal_mass=True, numbering=numbering)
+        H = syn.build_hierarchies(prob, max_coarse=40)
+        lp = part.distribute_problem(prob, H, 0, 1)
+        n = prob.A.shape[0]
+        order = lp.order0 if lp.order0 is not None else np.arange(n)
+        assert lp.block_size == 2 and lp.sizes_local == prob.sizes
+        assert (lp.mats[b.MAT_A].local != prob.A[order][:, order]).nnz == 0
+        assert (lp.mats[b.MAT_CT].local != prob.Ct[order]).nnz == 0
+        assert (lp.mats[b.MAT_C].local != sp.csr_matrix(prob.Ct[order].T)).nnz == 0
+        assert (lp.mats[b.MAT_BT].local != prob.Bt[order]).nnz == 0
+        assert (lp.mats[b.MAT_B].local != sp.csr_matrix(prob.Bt[order].T)).nnz == 0
+        assert (lp.mats[b.MAT_MP].local != prob.Mp).nnz == 0
+        for dc in lp.mats.values():
+            assert dc.plan is None or (dc.plan.n_halo == 0 and dc.plan.send_idx.size == 0)
+        LH = lp.amg[b.AMG_A11]
+        assert len(LH.levels) == len(H[b.AMG_A11].levels) - 1
+        L0, G0 = LH.levels[0], H[b.AMG_A11].levels[0]
+        assert (L0.A.local != G0.A[order][:, order]).nnz == 0
+        assert (L0.P.local != G0.P[order]).nnz == 0 and (L0.R.local != G0.R[:, order]).nnz == 0
+        assert np.array_equal(L0.inv_diag, G0.inv_diag[order]) and L0.lambda_max == G0.lambda_max
+        assert (LH.coarse_A != H[b.AMG_A11].levels[-1].A).nnz == 0
+        assert list(LH.coarse_off) == [0, LH.coarse_A.shape[0]]
+        x = np.random.default_rng(0).uniform(-1, 1, prob.n_dofs)
+        assert np.array_equal(lp.gather([lp.scatter(x)]), x)
