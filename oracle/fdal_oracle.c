@@ -6,20 +6,26 @@
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
  * may load this library; the product (libfdal.so, CUDA) never does.
  *
- * PARITY UNPINNED: the reference ships no tests, golden vectors or committed
- * iteration counts for this path, and its arithmetic lives in deal.II >= 9.6,
- * Trilinos ML >= 14.4 and UMFPACK, none of which is vendored under the
- * reference tree or installable here.  This file restates
- *   - the algebra of the five AL preconditioner vmults
- *     (augmented_lagrangian_preconditioner.h:28-34, 62-70, 95-103, 130-156, 225-228),
- *   - the operator definitions of the three applications
- *     (immersed_laplace.cc:880-905, stokes_immersed_boundary.cc:931-1018,
- *      elliptic_interface.cc:693-819),
- *   - deal.II's published SolverControl / ReductionControl /
- *     IterationNumberControl rules, SolverCG, SolverFGMRES, SolverMinRes and
- *     inverse_operator semantics,
- *   - the ML V-cycle with Chebyshev smoothing,
- * and is pinned only by algebraic known-answer checks (tests/test_oracle_*.py).
+ * PARITY: PARTLY PINNED.
+ *   PINNED against the reference's own code: the algebra of the five AL
+ *   preconditioner vmults (augmented_lagrangian_preconditioner.h:28-34, 62-70,
+ *   95-103, 130-156, 225-228).  That header is compiled UNMODIFIED from
+ *   /root/reference against stand-in deal.II vector/LinearOperator types
+ *   (oracle/ref_harness, `make ref` -> oracle/_ref/libref_prec.so) and its vmults
+ *   are run on seeded inputs; fdalo_apply_prec is bit-identical to them
+ *   (tests/test_reference_pinning.py) and the outputs are committed as
+ *   tests/golden/ref_prec_vectors.npz.
+ *   UNPINNED (restated from published algorithms, checked only by algebraic
+ *   known answers, tests/test_oracle_known_answers.py): everything whose
+ *   arithmetic lives in dependencies that are neither vendored under the
+ *   reference tree nor installable here — deal.II >= 9.6 (SolverControl /
+ *   ReductionControl / IterationNumberControl rules, SolverCG, SolverFGMRES,
+ *   SolverMinRes, inverse_operator, SparseMatrix::vmult/Tvmult; SURVEY.md App.
+ *   A.1-A.5, A.7), Trilinos ML >= 14.4 (V-cycle with Chebyshev smoothing, App.
+ *   A.6) and UMFPACK — and the operator definitions inside the three
+ *   applications (immersed_laplace.cc:880-905, stokes_immersed_boundary.cc:
+ *   931-1018, elliptic_interface.cc:693-819), which need all of deal.II to build.
+ *   The reference ships no tests, golden vectors or committed AL iteration counts.
  *
  * The API mirrors include/fdal.h with the prefix fdalo_ so the same Python
  * binding drives both sides of a parity test.  Exact mass inverses are direct

@@ -1,7 +1,8 @@
 """Regenerates tests/golden/oracle_regression.npz.
 
-There are NO reference-derived golden vectors for this path (the reference ships no
-tests and cannot be built here; DESIGN.md §2, "parity unpinned").  These fixtures are
+The reference-derived vectors live in ref_prec_vectors.npz (generate_ref_prec.py); the
+reference ships no tests and its applications cannot be built here, so
+there is no reference data for whole solves.  The fixtures of THIS file are
 produced by the CPU ORACLE itself on the seeded synthetic problems of tests/problems.py
 and only pin the oracle against accidental change (iteration counts, residual histories,
 solution checksums); they are not evidence of parity with deal.II / Trilinos.

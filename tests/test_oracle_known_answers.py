@@ -1,8 +1,9 @@
 """Known-answer checks that pin the CPU oracle (SURVEY.md 8(c) invariants).
 
-The reference ships no golden vectors (parity unpinned), so the oracle is pinned
-by algebra: each piece is compared with an independent numpy/scipy evaluation
-of the formula written in the reference source.
+The reference ships no golden vectors, so apart from the preconditioner classes
+(pinned against the compiled reference header in test_reference_pinning.py) the
+oracle is pinned by algebra: each piece is compared with an independent
+numpy/scipy evaluation of the formula written in the reference source.
 """
 import copy
 

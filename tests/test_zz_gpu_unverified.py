@@ -3,6 +3,7 @@ collected LAST (file name), so whatever they do cannot disturb the verified suit
 import pytest
 
 from . import problems as P
+from .golden.generate_ref_prec import REF_CASES
 from .test_gpu_parity import _pair
 
 pytestmark = pytest.mark.gpu
@@ -22,3 +23,45 @@ def test_extra_cases_not_yet_run_on_gpu(name, oracle_mod):
     assert abs(ig.outer_iterations - io.outer_iterations) <= 1
     if ig.outer_iterations == io.outer_iterations:
         assert P.relerr(xg, xo) < 1e-8
+
+
+# ---- reference-derived golden vectors (tests/golden/ref_prec_vectors.npz) through the C ABI ------
+# The same comparisons pass for the CPU oracle (tests/test_reference_pinning.py, bit-identical) and
+# the CUDA library matches the oracle on these inputs (test_gpu_parity), so these are expected to
+# pass; they were written after the last GPU run of round 1, hence non-strict xfail.
+@pytest.mark.xfail(strict=False, reason="written after the last GPU run of round 1")
+@pytest.mark.parametrize("name", [n for n in REF_CASES if n in P.CASES])
+def test_cuda_preconditioner_reproduces_the_reference_vectors(name, oracle_mod):
+    from .test_gpu_parity import _self_sensitivity
+    from .test_reference_pinning import GOLD
+
+    prob, gpu, ora = _pair(name, oracle_mod)
+    u = P.rand(prob.n_dofs, 10)
+    v, _ = gpu.apply_prec(u)
+    # reproducibility floor of the inner CG trajectories (see test_gpu_parity._self_sensitivity)
+    tol = max(1e-12, 50 * _self_sensitivity(lambda w: ora.apply_prec(w)[0], u, 2))
+    assert P.relerr(v, GOLD[f"{name}/v_ref"]) < tol
+
+
+@pytest.mark.xfail(strict=False, reason="written after the last GPU run of round 1")
+@pytest.mark.parametrize("name", ["laplace_diag", "laplace_exact", "stokes2d_exact", "stokes2d_diag", "stokes3d_diag",
+                                  "elliptic_modified", "elliptic_ideal", "elasticity", "stokes2d_node"])
+def test_cuda_with_tight_inner_solves_matches_exact_reference_vectors(name):
+    import copy
+
+    from fictitious_domain_al_preconditioners_b200 import ALContext
+    from fictitious_domain_al_preconditioners_b200 import synthetic as syn
+
+    from .test_reference_pinning import GOLD, tight_context
+
+    def make(prob, H, over):
+        cfg = copy.deepcopy(prob.config)
+        for k, val in over.items():
+            setattr(cfg, k, val)
+        p2 = copy.copy(prob)
+        p2.config = cfg
+        return syn.setup_context(ALContext(cfg), p2, H)
+
+    prob, ctx = tight_context(make, name)
+    v, _ = ctx.apply_prec(P.rand(prob.n_dofs, 13))
+    assert P.relerr(v, GOLD[f"{name}/v_exact"]) < 1e-8
