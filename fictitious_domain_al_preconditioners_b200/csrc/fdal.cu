@@ -217,6 +217,7 @@ struct fdal_ctx {
   char *flush_buf = nullptr;
   size_t flush_bytes = 0;
   double *mass_cta_ws = nullptr;       // 5*m scratch of k_mass_pcg_cta (m <= kMassCtaMaxRows)
+  double *d_winv_dense = nullptr;      // m x m exact W^-1 (opt-in FDAL_DENSE_WINV=1, m <= kDenseWinvMaxRows)
   int mass_its_m = 0, mass_its_p = 0;  // calibrated fixed iteration counts (exact mass solves)
   // counters
   int its_a11 = 0, its_a22 = 0, its_mass = 0, n_inner_solves = 0;
@@ -928,6 +929,11 @@ static void apply_winv_scaled(fdal_ctx *c, double a, const double *x, double *y,
     return;
   }
   const int repeat = c->cfg.winv_mode == FDAL_WINV_EXACT_M ? 1 : 2;
+  if (c->d_winv_dense) {
+    k_gemv_axpb<<<(int)((m * 32 + kBlock - 1) / kBlock), kBlock, 0, c->stream>>>((int)m, c->d_winv_dense, x, a, add, y);
+    c->launches++;
+    return;
+  }
   if (c->mass_cta_ws) {
     // whole fixed-count PCG (both applications of M^-1 for W = M^2) in one CTA
     const int threads = (int)std::min<int64_t>(kMassCtaThreads, ((m + 31) / 32) * 32);
@@ -1008,7 +1014,7 @@ static void apply_aug11(fdal_ctx *c, const double *x, double *y, double *dot_out
       spmv(c, A, x, EpiDotX{y, x}, dot_out);
     else
       spmv(c, A, x, EpiAssign{y, 1.0});
-  } else if (c->overlap_mass && c->mass_cta_ws && c->nranks == 1 && !gd) {
+  } else if (c->overlap_mass && c->mass_cta_ws && !c->d_winv_dense && c->nranks == 1 && !gd) {
     // exact W^-1: the mass solve is ONE CTA for ~90 us.  Fork: y = A x on the second stream
     // fills the other 147 SMs meanwhile; join: y += Ct t (+ fused x.y) over the few rows of Ct.
     // C x first, then fork: the one-CTA mass kernel is enqueued BEFORE the grid-filling A x
@@ -1407,6 +1413,55 @@ static int minres(fdal_ctx *c, const double *b, double *x, fdal_solve_info *info
 }
 
 // ------------------------------------------------------------------ finalize helpers
+// dense W^-1 of a small multiplier space (opt-in): Gauss-Jordan inverse of M on the device (same
+// kernels as the coarsest AMG operator), squared for W = M^2.  2 MB for the 514 multipliers of
+// configs[1]: it stays in L2 and one GEMV replaces the two ~45 us single-CTA mass solves.
+static const int64_t kDenseWinvMaxRows = 4096;
+static int build_dense_winv(fdal_ctx *c) {
+  const DevCsr &M = c->dmat[FDAL_MAT_M];
+  const int n = (int)c->m;
+  double *aug = nullptr, *col = nullptr, *pval = nullptr, *minv = nullptr;
+  int *prow = nullptr, *sing = nullptr;
+  int st;
+  if ((st = dvec(c, &aug, (int64_t)n * 2 * n))) return st;
+  if ((st = dvec(c, &col, n))) return st;
+  if ((st = dvec(c, &pval, 1))) return st;
+  if ((st = dmalloc(c, &prow, 1))) return st;
+  if ((st = dmalloc(c, &sing, 1))) return st;
+  if ((st = dmalloc(c, &minv, (size_t)n * n))) return st;
+  CU(cudaMemsetAsync(sing, 0, sizeof(int), c->stream));
+  const int tb = 256;
+  k_dense_from_csr<<<(n + tb - 1) / tb, tb, 0, c->stream>>>(n, M.rp, M.ci, M.v, aug);
+  const int gc = (2 * n + tb - 1) / tb;
+  for (int k = 0; k < n; ++k) {
+    k_gj_pivot<<<1, kBlock, 0, c->stream>>>(n, k, aug, prow, pval, sing);
+    k_gj_swap_scale<<<gc, tb, 0, c->stream>>>(n, k, aug, prow, pval);
+    k_gj_save_col<<<(n + tb - 1) / tb, tb, 0, c->stream>>>(n, k, aug, col);
+    k_gj_eliminate<<<dim3(gc, n), tb, 0, c->stream>>>(n, k, aug, col);
+  }
+  k_gj_extract<<<dim3((n + tb - 1) / tb, n), tb, 0, c->stream>>>(n, aug, minv);
+  int hs = 0;
+  CU(cudaMemcpyAsync(&hs, sing, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  cudaFree(aug);
+  c->allocs.erase(std::find(c->allocs.begin(), c->allocs.end(), (void *)aug));
+  if (hs) {
+    set_err(c, "immersed mass matrix is singular");
+    return FDAL_ERR_INVALID;
+  }
+  if (c->cfg.winv_mode == FDAL_WINV_EXACT_M) {
+    c->d_winv_dense = minv;
+    return FDAL_OK;
+  }
+  if ((st = dmalloc(c, &c->d_winv_dense, (size_t)n * n))) return st;
+  k_dense_square<<<dim3((n + tb - 1) / tb, n), tb, 0, c->stream>>>(n, minv, c->d_winv_dense);
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  cudaFree(minv);
+  c->allocs.erase(std::find(c->allocs.begin(), c->allocs.end(), (void *)minv));
+  return FDAL_OK;
+}
 static int invert_coarse(fdal_ctx *c, Amg &g) {
   AmgLevel &C = g.lev.back();
   const int n = g.cn_global;  // the coarsest operator is replicated on every rank
@@ -1818,6 +1873,8 @@ int fdal_finalize(fdal_ctx *c) {
     if ((st = mass_calibrate(c, c->cgmass_m, c->dmat[FDAL_MAT_M], c->d_m_invdiag, &c->mass_its_m))) return st;
     static const bool no_cta = getenv("FDAL_NO_MASS_CTA") != nullptr;
     if (c->m <= kMassCtaMaxRows && !no_cta && (st = dvec(c, &c->mass_cta_ws, 5 * c->m))) return st;
+    if (const char *e = getenv("FDAL_DENSE_WINV"))
+      if (atoi(e) > 0 && c->m > 0 && c->m <= kDenseWinvMaxRows && (st = build_dense_winv(c))) return st;
   }
   if (is_stokes(c)) {
     if ((st = alloc_cg(c, c->cgmass_p, c->n1))) return st;

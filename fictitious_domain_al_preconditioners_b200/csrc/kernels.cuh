@@ -486,6 +486,34 @@ __global__ void __launch_bounds__(kBlock) k_gemv(int nrows, int ncols, const dou
   s = warp_sum(s);
   if (lane == 0) y[warp] = s;
 }
+// y = a * (W x) (+ add) with a dense row-major n x n W: the exact W^-1 = M^-1 (or M^-2) of a small
+// multiplier space kept resident in L2 (opt-in, FDAL_DENSE_WINV; apply_winv_scaled).  One warp per row.
+__global__ void __launch_bounds__(kBlock) k_gemv_axpb(int n, const double *__restrict__ W, const double *__restrict__ x,
+                                                       double a, const double *__restrict__ add,
+                                                       double *__restrict__ y) {
+  const int warp = (blockIdx.x * kBlock + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n) return;
+  const double *row = W + (size_t)warp * n;
+  double s0 = 0.0, s1 = 0.0;
+  int k = lane;
+  for (; k + 32 < n; k += 64) {
+    s0 += __ldg(row + k) * __ldg(x + k);
+    s1 += __ldg(row + k + 32) * __ldg(x + k + 32);
+  }
+  if (k < n) s0 += __ldg(row + k) * __ldg(x + k);
+  const double s = warp_sum(s0 + s1);
+  if (lane == 0) y[warp] = a * s + (add ? add[warp] : 0.0);
+}
+// C = A A for a dense row-major n x n A (setup, once: M^-2 from M^-1)
+__global__ void k_dense_square(int n, const double *__restrict__ A, double *__restrict__ C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  if (c >= n) return;
+  const double *row = A + (size_t)r * n;
+  double s = 0.0;
+  for (int k = 0; k < n; ++k) s += row[k] * A[(size_t)k * n + c];
+  C[(size_t)r * n + c] = s;
+}
 // halo pack: buf[i] = x[idx[i]]
 __global__ void __launch_bounds__(kBlock) k_pack(int n, const int *__restrict__ idx, const double *__restrict__ x,
                                                   double *__restrict__ buf) {
