@@ -417,6 +417,79 @@ def immersed_laplace(
     return prob
 
 
+def nitsche_bcs(r: int = 5, multiplier_degree: int = 1, gamma: float = 10.0, manufactured: bool = True) -> Problem:
+    """2x2 system of the fourth application, nitsche_bcs (Dirichlet data imposed weakly by a
+    boundary multiplier; "next" row N4 of SURVEY 8(f)): the SAME BlockPreconditionerAugmented-
+    Lagrangian path as immersed_laplace in operator form (nitsche_bcs.cc:497-661).
+
+    Unit square, Q1 bulk space WITHOUT strong boundary conditions, multiplier space on the boundary
+    mesh extracted from the bulk mesh (matching): continuous P1 (``multiplier_degree=1``) or the
+    shipped discontinuous P0 (``=0``, parameters_nitsche.prm — its coupling matrix has the
+    alternating multiplier in its kernel, so only the Krylov solve is meaningful there).
+      stiffness  A = (grad u, grad v) + (gamma/h) <u, v>_boundary     (:531-566, explicit AL term)
+      invW       = (1/h) M_b^-1  (UMFPACK)                             (:637-640)
+      P          = BlockPreconditionerAugmentedLagrangian{A_inv, ., ., invW, gamma}  (:642)
+    which is kind LAPLACE with aug_explicit, WINV_EXACT_M and gamma_eff = gamma / h.  The right-hand
+    side carries the consistent augmentation (gamma/h) <g, v>_boundary itself (:575-632)."""
+    nel = 2**r
+    h = 1.0 / nel
+    n1 = nel + 1
+    K1, M1 = fe1d(nel, h, 1, 1, 1, 1), fe1d(nel, h, 1, 1)
+    A0 = kron_all([M1, K1]) + kron_all([K1, M1])
+    Mbg = kron_all([M1, M1])
+    n = n1 * n1
+    # boundary loop, counter-clockwise from the origin: 4 nel nodes / 4 nel edges
+    k = np.arange(nel)
+    ix = np.concatenate([k, np.full(nel, nel), nel - k, np.zeros(nel, int)])
+    iy = np.concatenate([np.zeros(nel, int), k, np.full(nel, nel), nel - k])
+    loop = ix + n1 * iy
+    nb = 4 * nel
+    E = sp.csr_matrix((np.ones(nb), (loop, np.arange(nb))), shape=(n, nb))  # bulk dof <- boundary node
+    nxt = (np.arange(nb) + 1) % nb
+    # P1 trace mass on the closed loop
+    Mtrace = sp.coo_matrix(
+        (np.concatenate([np.full(nb, 2 * h / 3), np.full(nb, h / 6), np.full(nb, h / 6)]),
+         (np.concatenate([np.arange(nb), np.arange(nb), nxt]), np.concatenate([np.arange(nb), nxt, np.arange(nb)]))),
+        shape=(nb, nb)).tocsr()
+    if multiplier_degree == 1:
+        M = _csr(Mtrace)
+        Ct = _csr(E @ Mtrace)  # <phi_i, mu_j>: the trace of a bulk hat function is the boundary hat function
+    else:
+        M = _csr(sp.diags(np.full(nb, h)))
+        # edge j joins boundary nodes j and j+1: int_e phi = h/2 for both
+        Half = sp.coo_matrix((np.full(2 * nb, h / 2), (np.concatenate([np.arange(nb), nxt]), np.tile(np.arange(nb), 2))),
+                             shape=(nb, nb)).tocsr()
+        Ct = _csr(E @ Half)
+    g_eff = gamma / h  # invW_scale = 1 / h_immersed (:519-522)
+    A = _csr(A0 + g_eff * (E @ Mtrace @ E.T))
+    X, Y = np.meshgrid(np.linspace(0, 1, n1), np.linspace(0, 1, n1), indexing="xy")
+    x, y = X.ravel(), Y.ravel()
+    if manufactured:
+        u_exact = np.sin(np.pi * x) * np.cos(np.pi * y) + x
+        f_nodal = 2 * np.pi**2 * np.sin(np.pi * x) * np.cos(np.pi * y)
+    else:  # parameters_nitsche.prm: f = 1, g = x^2 + y^2
+        u_exact = None
+        f_nodal = np.ones(n)
+    g_nodal = (u_exact if manufactured else x * x + y * y)[loop]
+    rhs0 = Mbg @ f_nodal + g_eff * (E @ (Mtrace @ g_nodal))
+    rhs1 = Ct.T @ (E @ g_nodal)  # <g_h, mu_j> with g_h the nodal interpolant on the boundary
+    cfg = ALConfig(
+        kind=b.KIND_LAPLACE,
+        restart=30,
+        gamma=g_eff,
+        aug_explicit=True,
+        winv_mode=b.WINV_EXACT_M,
+        inner=ReductionControl(1000, 1e-2, 1e-10),   # parameters_nitsche.prm "Inner solver control"
+        outer=ReductionControl(1000, 1e-12, 1e-9),   # "Outer solver control"
+    )
+    prob = Problem(name=f"nitsche_bcs_r{r}_p{multiplier_degree}", config=cfg, A=A, Ct=Ct, M=M,
+                   rhs=np.concatenate([rhs0, rhs1]), augment_rhs=False)
+    prob.amg_matrix[b.AMG_A11] = prob.A  # amg_prec.initialize(stiffness_matrix) (:568)
+    prob.amg_theta[b.AMG_A11] = 1e-4
+    prob.meta = dict(h=h, n_bg=n, m=nb, u_exact=u_exact, boundary_dofs=loop)
+    return prob
+
+
 # ----------------------------------------------------------------------------- fast velocity block
 def velocity_block_tensor(nel: int, dim: int, gamma_grad_div: float, bnd_s: np.ndarray, device=None,
                           interleaved: bool = False, p: int = 2, length: float = 1.0, terms=None) -> sp.csr_matrix:

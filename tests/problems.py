@@ -36,6 +36,9 @@ EXTRA_CASES = {
     # (stokes_immersed_boundary.cc:992-995, 1046-1051)
     "stokes2d_nogd": (syn.stokes_immersed_boundary, dict(dim=2, nel=8, grad_div_stabilization=False, diagonal_mass=True)),
     "stokes2d_nogd_exact": (syn.stokes_immersed_boundary, dict(dim=2, nel=8, grad_div_stabilization=False)),
+    # the fourth application, nitsche_bcs: same 2x2 path, explicit AL term, invW = M_b^-1 / h
+    "nitsche_p1": (syn.nitsche_bcs, dict(r=5, multiplier_degree=1)),
+    "nitsche_p0": (syn.nitsche_bcs, dict(r=5, multiplier_degree=0, manufactured=False)),  # parameters_nitsche.prm
 }
 
 

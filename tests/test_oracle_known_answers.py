@@ -352,3 +352,37 @@ def test_constraint_is_satisfied(oracle_mod):
     n, m = prob.Ct.shape
     d = prob.M @ x[n:n + m] - prob.Ct.T @ x[:n]
     assert np.abs(d).max() < 1e-8
+
+
+def test_nitsche_bcs_converges_to_the_manufactured_solution(oracle_mod):
+    """nitsche_bcs through the 2x2 AL path: the FGMRES solution equals the sparse
+    direct solution of the saddle-point system, approaches the manufactured solution at O(h^2), and the
+    outer iteration count does not grow with refinement."""
+    errs, outer = [], []
+    for r in (3, 4, 5):
+        prob = syn.nitsche_bcs(r)
+        H = syn.build_hierarchies(prob, max_coarse=40)
+        ctx = syn.setup_context(oracle_mod.OracleContext(prob.config), prob, H, oracle=True)
+        x, info = ctx.solve(prob.rhs)
+        n = prob.sizes[0]
+        K = sp.bmat([[prob.A, prob.Ct], [prob.Ct.T, None]]).tocsc()
+        xd = spla.spsolve(K, prob.rhs)
+        assert info.status == 0 and P.relerr(x, xd) < 1e-4
+        errs.append(np.sqrt(np.mean((x[:n] - prob.meta["u_exact"]) ** 2)))
+        outer.append(info.outer_iterations)
+    assert errs[1] < errs[0] / 3.5 and errs[2] < errs[1] / 3.5
+    assert max(outer) <= 8
+
+
+def test_nitsche_bcs_shipped_p0_multiplier_converges(oracle_mod):
+    """parameters_nitsche.prm: discontinuous P0 multipliers; the alternating multiplier is in the kernel of
+    the coupling matrix, FGMRES still reduces the residual of the consistent system by 1e-9."""
+    prob = syn.nitsche_bcs(4, multiplier_degree=0, manufactured=False)
+    alt = (-1.0) ** np.arange(prob.sizes[1])
+    assert np.abs(prob.Ct @ alt).max() < 1e-14
+    H = syn.build_hierarchies(prob, max_coarse=40)
+    ctx = syn.setup_context(oracle_mod.OracleContext(prob.config), prob, H, oracle=True)
+    x, info = ctx.solve(prob.rhs)
+    assert info.status == 0 and info.final_residual <= 1e-9 * info.initial_residual * 1.01
+    r = prob.rhs - np.concatenate([prob.A @ x[: prob.sizes[0]] + prob.Ct @ x[prob.sizes[0]:], prob.Ct.T @ x[: prob.sizes[0]]])
+    assert np.linalg.norm(r) <= 1e-8 * np.linalg.norm(prob.rhs)

@@ -8,7 +8,7 @@ from .properties import check_properties
 
 
 @pytest.mark.parametrize("name", ["laplace_diag", "stokes2d_diag", "stokes2d_exact", "stokes3d_node", "elliptic_modified_diag",
-                                  "stokes2d_nogd", "stokes2d_nogd_exact"])
+                                  "stokes2d_nogd", "stokes2d_nogd_exact", "nitsche_p1"])
 def test_properties_hold_for_the_oracle(name, oracle_mod):
     prob, H = P.get(name)
     ora = syn.setup_context(oracle_mod.OracleContext(prob.config), prob, H, oracle=True)
