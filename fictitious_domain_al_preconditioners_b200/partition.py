@@ -369,11 +369,46 @@ def setup_local_context(ctx, lp: LocalProblem, uid: bytes = bytes(128)):
     return ctx
 
 
+def plan_signature(lp: LocalProblem) -> dict:
+    """(send_counts, recv_counts) of every halo plan of one rank, keyed by matrix."""
+    sig = {}
+    for mid, dc in lp.mats.items():
+        if dc.plan is not None:
+            sig[("mat", mid)] = (dc.plan.send_counts.copy(), dc.plan.recv_counts.copy())
+    for which, LH in lp.amg.items():
+        for l, L in enumerate(LH.levels):
+            for tag, dc in (("A", L.A), ("P", L.P), ("R", L.R)):
+                if dc is not None and dc.plan is not None:
+                    sig[("amg", which, l, tag)] = (dc.plan.send_counts.copy(), dc.plan.recv_counts.copy())
+    return sig
+
+
+def check_plan_signatures(sigs: list) -> None:
+    """What rank p sends to q is what q expects from p, for every partitioned matrix.  A mismatch
+    would leave the grouped ncclSend/ncclRecv of halo_exchange waiting forever, so it is refused on
+    the host before any context is built."""
+    nranks = len(sigs)
+    keys = set(sigs[0])
+    for r, sg in enumerate(sigs):
+        if set(sg) != keys:
+            raise ValueError(f"rank {r} has halo plans for {sorted(set(sg) ^ keys)} that rank 0 lacks (or vice versa)")
+    for key in sorted(keys, key=str):
+        for p_ in range(nranks):
+            send = sigs[p_][key][0]
+            for q in range(nranks):
+                if int(send[q]) != int(sigs[q][key][1][p_]):
+                    raise ValueError(f"halo plan mismatch for {key}: rank {p_} sends {int(send[q])} entries to rank {q}, "
+                                     f"which expects {int(sigs[q][key][1][p_])}")
+            if int(send[p_]) != 0:
+                raise ValueError(f"halo plan for {key}: rank {p_} sends to itself")
+
+
 def distribute_all(prob, hierarchies: dict, nranks: int) -> list:
     """Every rank's LocalProblem, cut on one process."""
     D = Distributor(prob, hierarchies, nranks)
     out = [D.local(r) for r in range(nranks)]
     clear_cache()
+    check_plan_signatures([plan_signature(lp) for lp in out])
     return out
 
 
@@ -399,8 +434,10 @@ def share_local_problems(build_fn, rank: int, nranks: int, group=None):
             base = max(cands, key=lambda p_: shutil.disk_usage(p_).free) if cands else None
             d = tempfile.mkdtemp(prefix="fdal_lp_", dir=base)
             D = Distributor(prob, H, nranks)
+            sigs = []
             for r in range(nranks):
                 lp = D.local(r)
+                sigs.append(plan_signature(lp))
                 lp.rhs_local = lp.scatter(prob.rhs)
                 lp.augment_rhs = bool(prob.augment_rhs)
                 lp.meta = dict(meta)
@@ -409,6 +446,7 @@ def share_local_problems(build_fn, rank: int, nranks: int, group=None):
                 del lp
             clear_cache()
             del prob, H, D
+            check_plan_signatures(sigs)
             box[0] = d
         except Exception as e:  # tell the other ranks instead of leaving them in the broadcast
             import traceback

@@ -290,3 +290,17 @@ def test_single_rank_share_is_the_renumbered_problem():
         assert list(LH.coarse_off) == [0, LH.coarse_A.shape[0]]
         x = np.random.default_rng(0).uniform(-1, 1, prob.n_dofs)
         assert np.array_equal(lp.gather([lp.scatter(x)]), x)
+
+
+def test_inconsistent_halo_plans_are_refused_on_the_host():
+    """A plan in which one rank sends what its peer does not expect would deadlock the grouped
+    send/recv on the GPUs; check_plan_signatures turns it into an error before any context exists."""
+    prob = syn.stokes_immersed_boundary(dim=2, nel=8, diagonal_mass=True, numbering="node")
+    H = syn.build_hierarchies(prob, max_coarse=40)
+    lps = part.distribute_all(prob, H, 3)  # validates internally
+    sigs = [part.plan_signature(lp) for lp in lps]
+    assert any(k[0] == "amg" for k in sigs[0]) and ("mat", b.MAT_A) in sigs[0]
+    part.check_plan_signatures(sigs)
+    sigs[1][("mat", b.MAT_A)][0][0] += 1
+    with pytest.raises(ValueError, match="halo plan mismatch"):
+        part.check_plan_signatures(sigs)
