@@ -517,6 +517,8 @@ static void spmv_bsr(fdal_ctx *c, const DevCsr &A, const double *x, const DevCsr
   do {                                                                                              \
     if (!A.bsr.aos)                                                                                 \
       k_bsr_spmv<BB, TT, Epi, TWO, false><<<g, kBlock, 0, c->stream>>>(A.bsr, X, b2, t2, epi, R);   \
+    else if (c->bsr_unroll >= 4)                                                                    \
+      k_bsr_spmv<BB, TT, Epi, TWO, true, 4><<<g, kBlock, 0, c->stream>>>(A.bsr, X, b2, t2, epi, R); \
     else if (c->bsr_unroll > 1)                                                                     \
       k_bsr_spmv<BB, TT, Epi, TWO, true, 2><<<g, kBlock, 0, c->stream>>>(A.bsr, X, b2, t2, epi, R); \
     else                                                                                            \
