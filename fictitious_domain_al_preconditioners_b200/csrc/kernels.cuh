@@ -291,6 +291,16 @@ __global__ void __launch_bounds__(kBlock) k_bsr_spmv(BsrDev A, XVec X, CsrDev C2
   const int lane = threadIdx.x & (TPR - 1);
   const int local_row = threadIdx.x / TPR;
   double contrib = 0.0;
+  // U >= 4 (opt-in variant): the block-row pointers of the NEXT grid-stride step are fetched while
+  // this step's blocks are in flight, which takes one DRAM latency out of every step's chain
+  int k0n = 0, k1n = 0;
+  if constexpr (U >= 4) {
+    const long long I0 = (long long)blockIdx.x * rows_per_block + local_row;
+    if (I0 < A.nbrows) {
+      k0n = __ldg(A.rp + I0);
+      k1n = __ldg(A.rp + I0 + 1);
+    }
+  }
   for (long long base = (long long)blockIdx.x * rows_per_block; base < A.nbrows;
        base += (long long)gridDim.x * rows_per_block) {
     const long long I = base + local_row;
@@ -298,7 +308,19 @@ __global__ void __launch_bounds__(kBlock) k_bsr_spmv(BsrDev A, XVec X, CsrDev C2
 #pragma unroll
     for (int r = 0; r < B; ++r) s[r] = 0.0;
     if (I < A.nbrows) {
-      const int k0 = __ldg(A.rp + I), k1 = __ldg(A.rp + I + 1);
+      int k0, k1;
+      if constexpr (U >= 4) {
+        k0 = k0n;
+        k1 = k1n;
+        const long long In = I + (long long)gridDim.x * rows_per_block;
+        if (In < A.nbrows) {
+          k0n = __ldg(A.rp + In);
+          k1n = __ldg(A.rp + In + 1);
+        }
+      } else {
+        k0 = __ldg(A.rp + I);
+        k1 = __ldg(A.rp + I + 1);
+      }
       const int nb = k1 - k0;
       const double *vb = A.v + (size_t)k0 * (B * B);
       for (int kk = lane; kk < nb; kk += U * TPR) {
