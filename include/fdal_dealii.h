@@ -1,9 +1,12 @@
 /*
  * fdal_dealii.h — header-only adapter between deal.II / Trilinos objects and the C ABI of
- * fdal.h.  NOT COMPILED IN THIS REPOSITORY: deal.II (>= 9.6), Trilinos ML and UMFPACK are not
- * installed in the build image, so this file is the reference-side binding a
- * maintainer adds next to augmented_lagrangian_preconditioner.h; the Python mirror
- * (fictitious_domain_al_preconditioners_b200/operators.py) exercises the same entry points.
+ * fdal.h: the reference-side binding a maintainer adds next to
+ * augmented_lagrangian_preconditioner.h.  deal.II (>= 9.6), Trilinos ML and UMFPACK are not
+ * installed in the build image, so it has never been compiled against the real
+ * libraries.  What IS compiled and run here (tests/test_dealii_adapter.py): everything except
+ * export_amg (-DFDAL_DEALII_NO_TRILINOS), against the stand-in deal.II types of
+ * oracle/ref_harness/dealii_stub, together with the reference's own preconditioner classes —
+ * the reference class built from this adapter's LinearOperators reproduces fdal_apply_prec.
  *
  * What it provides:
  *   fdal_dealii::export_csr          dealii::SparseMatrix<double>            -> fdal_set_csr
@@ -30,8 +33,10 @@
 #include <deal.II/lac/trilinos_precondition.h>
 #include <deal.II/lac/vector.h>
 
+#ifndef FDAL_DEALII_NO_TRILINOS
 #include <ml_MultiLevelPreconditioner.h>
 #include <ml_epetra_utils.h>
+#endif
 
 #include <memory>
 #include <vector>
@@ -64,6 +69,7 @@ inline void export_csr(fdal_ctx *ctx, const int matrix_id, const dealii::SparseM
                           v.data()));
 }
 
+#ifndef FDAL_DEALII_NO_TRILINOS
 struct OwnedCsr {
   std::vector<int64_t> rp;
   std::vector<int32_t> ci;
@@ -122,6 +128,8 @@ inline void export_amg(fdal_ctx *ctx, const int which, const dealii::TrilinosWra
     delete R;
   }
 }
+
+#endif /* FDAL_DEALII_NO_TRILINOS */
 
 inline fdal_control to_control(const dealii::SolverControl &c) {
   fdal_control out{FDAL_CONTROL_SOLVER, static_cast<int32_t>(c.max_steps()), c.tolerance(), 0.0};
@@ -205,6 +213,91 @@ inline dealii::LinearOperator<dealii::Vector<double>> augmented_inverse(fdal_ctx
     check(ctx, st);
   };
   op.reinit_range_vector = op.reinit_domain_vector = [n](dealii::Vector<double> &v, bool fast) { v.reinit(n, fast); };
+  return op;
+}
+
+/* The "ideal" elliptic preconditioner takes Aug_inv as a LinearOperator on the first TWO blocks
+ * (elliptic_interface.cc:930-942; augmented_lagrangian_preconditioner.h:118,152).  With a zero
+ * multiplier residual the preconditioner's own vmult is exactly that block solve (header lines
+ * 135-155 with u.block(2) = 0), so it is served by fdal_apply_prec on [x0 | x1 | 0]. */
+inline dealii::LinearOperator<dealii::BlockVector<double>> augmented_block_inverse(fdal_ctx *ctx, const unsigned int n0,
+                                                                                   const unsigned int n1,
+                                                                                   const unsigned int n_lambda) {
+  dealii::LinearOperator<dealii::BlockVector<double>> op;
+  auto reinit = [n0, n1](dealii::BlockVector<double> &v, bool fast) {
+    v.reinit(2);
+    v.block(0).reinit(n0, fast);
+    v.block(1).reinit(n1, fast);
+    v.collect_sizes();
+  };
+  op.reinit_range_vector = op.reinit_domain_vector = reinit;
+  op.vmult = [ctx, n0, n1, n_lambda](dealii::BlockVector<double> &y, const dealii::BlockVector<double> &x) {
+    std::vector<double> u(n0 + n1 + n_lambda, 0.0), v(n0 + n1 + n_lambda);
+    std::copy(x.block(0).begin(), x.block(0).end(), u.begin());
+    std::copy(x.block(1).begin(), x.block(1).end(), u.begin() + n0);
+    int its[2] = {0, 0};
+    const int st = fdal_apply_prec(ctx, u.data(), v.data(), its);
+    if (st == FDAL_ERR_INNER_NO_CONVERGENCE) throw dealii::SolverControl::NoConvergence(its[0], 0.);
+    check(ctx, st);
+    std::copy(v.begin(), v.begin() + n0, y.block(0).begin());
+    std::copy(v.begin() + n0, v.begin() + n0 + n1, y.block(1).begin());
+  };
+  return op;
+}
+
+/* linear_operator(matrix) / transpose_operator(...) of an exported block, applied on the device:
+ * C, Ct, Bt, M of immersed_laplace.cc:638-642, stokes_immersed_boundary.cc:923-929,
+ * elliptic_interface.cc:680-687.  `transpose` selects SparseMatrix::Tvmult. */
+inline dealii::LinearOperator<dealii::Vector<double>> matrix_operator(fdal_ctx *ctx, const int matrix_id,
+                                                                      const bool transpose, const unsigned int n_range,
+                                                                      const unsigned int n_domain) {
+  dealii::LinearOperator<dealii::Vector<double>> op;
+  op.vmult = [ctx, matrix_id, transpose](dealii::Vector<double> &y, const dealii::Vector<double> &x) {
+    check(ctx, fdal_spmv(ctx, matrix_id, transpose ? 1 : 0, x.begin(), y.begin()));
+  };
+  op.Tvmult = [ctx, matrix_id, transpose](dealii::Vector<double> &y, const dealii::Vector<double> &x) {
+    check(ctx, fdal_spmv(ctx, matrix_id, transpose ? 0 : 1, x.begin(), y.begin()));
+  };
+  op.vmult_add = [vm = op.vmult, n_range](dealii::Vector<double> &y, const dealii::Vector<double> &x) {
+    dealii::Vector<double> t(n_range);
+    vm(t, x);
+    y += t;
+  };
+  op.Tvmult_add = [tvm = op.Tvmult, n_domain](dealii::Vector<double> &y, const dealii::Vector<double> &x) {
+    dealii::Vector<double> t(n_domain);
+    tvm(t, x);
+    y += t;
+  };
+  op.reinit_range_vector = [n_range](dealii::Vector<double> &v, bool fast) { v.reinit(n_range, fast); };
+  op.reinit_domain_vector = [n_domain](dealii::Vector<double> &v, bool fast) { v.reinit(n_domain, fast); };
+  return op;
+}
+/* invW (immersed_laplace.cc:849-878, stokes_immersed_boundary.cc:966-985, elliptic_interface.cc:693-739) */
+inline dealii::LinearOperator<dealii::Vector<double>> winv_operator(fdal_ctx *ctx, const unsigned int m) {
+  dealii::LinearOperator<dealii::Vector<double>> op;
+  op.vmult = [ctx](dealii::Vector<double> &y, const dealii::Vector<double> &x) {
+    check(ctx, fdal_apply_winv(ctx, x.begin(), y.begin()));
+  };
+  op.Tvmult = op.vmult; /* symmetric */
+  op.vmult_add = op.Tvmult_add = [ctx, m](dealii::Vector<double> &y, const dealii::Vector<double> &x) {
+    dealii::Vector<double> t(m);
+    check(ctx, fdal_apply_winv(ctx, x.begin(), t.begin()));
+    y += t;
+  };
+  op.reinit_range_vector = op.reinit_domain_vector = [m](dealii::Vector<double> &v, bool fast) { v.reinit(m, fast); };
+  return op;
+}
+/* Mp_inv (stokes_immersed_boundary.cc:931-963): inner CG failure -> SolverControl::NoConvergence */
+inline dealii::LinearOperator<dealii::Vector<double>> mp_inv_operator(fdal_ctx *ctx, const unsigned int n_p) {
+  dealii::LinearOperator<dealii::Vector<double>> op;
+  op.vmult = [ctx](dealii::Vector<double> &y, const dealii::Vector<double> &x) {
+    int its = 0;
+    const int st = fdal_apply_mp_inv(ctx, x.begin(), y.begin(), &its);
+    if (st == FDAL_ERR_MASS_NO_CONVERGENCE) throw dealii::SolverControl::NoConvergence(its, 0.);
+    check(ctx, st);
+  };
+  op.Tvmult = op.vmult;
+  op.reinit_range_vector = op.reinit_domain_vector = [n_p](dealii::Vector<double> &v, bool fast) { v.reinit(n_p, fast); };
   return op;
 }
 

@@ -1,2 +1,2 @@
 /* stand-in header, see stub_core.h (test infrastructure) */
-#include "stub_core.h"
+#include <deal.II/lac/stub_core.h>

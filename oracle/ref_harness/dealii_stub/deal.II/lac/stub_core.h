@@ -28,13 +28,52 @@
 
 namespace dealii {
 
-#define Assert(cond, exc)                                                         \
-  do {                                                                            \
-    if (!(cond)) throw std::runtime_error(std::string("Assert failed: ") + #cond); \
+/* exceptions: deal.II's Assert / AssertThrow throw the exception object they are handed */
+struct ExcMessage : std::runtime_error {
+  explicit ExcMessage(const std::string &m) : std::runtime_error(m) {}
+};
+inline ExcMessage ExcDimensionMismatch(const std::size_t a, const std::size_t b) {
+  return ExcMessage("dimension mismatch: " + std::to_string(a) + " != " + std::to_string(b));
+}
+inline ExcMessage ExcNotInitialized() { return ExcMessage("not initialized"); }
+#define Assert(cond, exc) \
+  do {                    \
+    if (!(cond)) throw exc; \
   } while (0)
 #define AssertThrow(cond, exc) Assert(cond, exc)
-inline int ExcDimensionMismatch(std::size_t, std::size_t) { return 0; }
-inline int ExcNotInitialized() { return 0; }
+
+/* SolverControl family: only what an adapter reads (limits) and throws (NoConvergence) */
+class SolverControl {
+ public:
+  class NoConvergence : public std::exception {
+   public:
+    NoConvergence(const unsigned int step, const double residual) : last_step(step), last_residual(residual) {}
+    const char *what() const noexcept override { return "SolverControl::NoConvergence"; }
+    const unsigned int last_step;
+    const double last_residual;
+  };
+  explicit SolverControl(const unsigned int n = 100, const double tol = 1.e-10) : maxsteps(n), tol_(tol) {}
+  virtual ~SolverControl() = default;
+  unsigned int max_steps() const { return maxsteps; }
+  double tolerance() const { return tol_; }
+
+ private:
+  unsigned int maxsteps;
+  double tol_;
+};
+class ReductionControl : public SolverControl {
+ public:
+  explicit ReductionControl(const unsigned int n = 100, const double tol = 1.e-10, const double red = 1.e-2)
+      : SolverControl(n, tol), reduce(red) {}
+  double reduction() const { return reduce; }
+
+ private:
+  double reduce;
+};
+class IterationNumberControl : public SolverControl {
+ public:
+  explicit IterationNumberControl(const unsigned int n = 100, const double tol = 1.e-12) : SolverControl(n, tol) {}
+};
 
 template <typename Range>
 class PackagedOperation;
@@ -142,6 +181,56 @@ class BlockVector {
 
  private:
   std::vector<BlockType> blocks;
+};
+
+/* SparseMatrix<double>: CSR with deal.II's accessor-style row iterators (column(), value()) */
+template <typename Number>
+class SparseMatrix {
+ public:
+  using size_type = std::size_t;
+  struct Accessor {
+    const SparseMatrix *A;
+    size_type k;
+    size_type column() const { return A->colnums[k]; }
+    Number value() const { return A->val[k]; }
+  };
+  class const_iterator {
+   public:
+    const_iterator(const SparseMatrix *A, size_type k) : acc{A, k} {}
+    const Accessor *operator->() const { return &acc; }
+    const Accessor &operator*() const { return acc; }
+    const_iterator &operator++() {
+      ++acc.k;
+      return *this;
+    }
+    bool operator!=(const const_iterator &o) const { return acc.k != o.acc.k; }
+    bool operator==(const const_iterator &o) const { return acc.k == o.acc.k; }
+
+   private:
+    Accessor acc;
+  };
+  SparseMatrix() = default;
+  SparseMatrix(size_type rows, size_type cols, std::vector<size_type> rowstart_, std::vector<unsigned int> colnums_,
+               std::vector<Number> val_)
+      : n_rows(rows), n_cols(cols), rowstart(std::move(rowstart_)), colnums(std::move(colnums_)), val(std::move(val_)) {}
+  size_type m() const { return n_rows; }
+  size_type n() const { return n_cols; }
+  size_type n_nonzero_elements() const { return val.size(); }
+  const_iterator begin(const size_type r) const { return const_iterator(this, rowstart[r]); }
+  const_iterator end(const size_type r) const { return const_iterator(this, rowstart[r + 1]); }
+  void vmult(Vector<Number> &y, const Vector<Number> &x) const {
+    for (size_type r = 0; r < n_rows; ++r) {
+      Number s = 0;
+      for (size_type k = rowstart[r]; k < rowstart[r + 1]; ++k) s += val[k] * x[colnums[k]];
+      y[r] = s;
+    }
+  }
+
+ private:
+  size_type n_rows = 0, n_cols = 0;
+  std::vector<size_type> rowstart;
+  std::vector<unsigned int> colnums;
+  std::vector<Number> val;
 };
 
 /* ------------------------------------------------------------------ LinearOperator */
