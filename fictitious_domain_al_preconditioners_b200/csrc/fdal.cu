@@ -361,6 +361,7 @@ static int build_bsr(fdal_ctx *c, const HostCsr &h, int b, DevCsr &d, bool *done
     const int t = atoi(e);
     if (t == 2 || t == 4 || t == 8 || t == 16) d.bsr.tpr = t;
   }
+  if (d.bsr.tpr < b) d.bsr.tpr = 4;  // the B epilogue lanes of a row group must exist
   d.bsr_b = b;
   d.bsr_nblocks = nblk;
   d.use_bsr = true;

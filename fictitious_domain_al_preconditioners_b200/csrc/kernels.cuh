@@ -14,6 +14,7 @@
 // K8 PreconditionAMG::vmult (Chebyshev steps, residual, restriction, prolongation),
 // K9/K10/K11 the Vector BLAS-1 inside SolverCG / SolverFGMRES.
 #pragma once
+#include <type_traits>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -117,6 +118,14 @@ struct EpiAdd {  // y += alpha * A x
     y[i] += alpha * s;
     return 0.0;
   }
+  struct Pre {
+    double yi;
+  };
+  __device__ Pre prefetch(int i) const { return Pre{y[i]}; }
+  __device__ double finish(int i, double s, const Pre &p) const {
+    y[i] = p.yi + alpha * s;
+    return 0.0;
+  }
 };
 struct EpiResid {  // y = b - A x     (also u0 - Ct v1 in the preconditioners)
   double *y;
@@ -124,6 +133,14 @@ struct EpiResid {  // y = b - A x     (also u0 - Ct v1 in the preconditioners)
   static constexpr bool kReduce = false;
   __device__ double operator()(int i, double s) const {
     y[i] = b[i] - s;
+    return 0.0;
+  }
+  struct Pre {
+    double bi;
+  };
+  __device__ Pre prefetch(int i) const { return Pre{b[i]}; }
+  __device__ double finish(int i, double s, const Pre &p) const {
+    y[i] = p.bi - s;
     return 0.0;
   }
 };
@@ -154,6 +171,15 @@ struct EpiAddDotX {  // y += A x ; reduce x_i * y_i  (joins the overlapped augme
     y[i] = yn;
     return x[i] * yn;
   }
+  struct Pre {
+    double yi, xi;
+  };
+  __device__ Pre prefetch(int i) const { return Pre{y[i], x[i]}; }
+  __device__ double finish(int i, double s, const Pre &p) const {
+    const double yn = p.yi + s;
+    y[i] = yn;
+    return p.xi * yn;
+  }
 };
 struct EpiDotX {  // y = A x ; reduce x_i * y_i  (p.Ap of CG)
   double *y;
@@ -162,6 +188,14 @@ struct EpiDotX {  // y = A x ; reduce x_i * y_i  (p.Ap of CG)
   __device__ double operator()(int i, double s) const {
     y[i] = s;
     return x[i] * s;
+  }
+  struct Pre {
+    double xi;
+  };
+  __device__ Pre prefetch(int i) const { return Pre{x[i]}; }
+  __device__ double finish(int i, double s, const Pre &p) const {
+    y[i] = s;
+    return p.xi * s;
   }
 };
 // fused Chebyshev step: r = b - A x ; d = c1 d + c2 D^-1 r ; xout = xin + d
@@ -182,6 +216,30 @@ struct EpiCheb {
     xout[i] = xo;
     return REDUCE ? bi * xo : 0.0;  // r.z of the enclosing CG when b is the CG residual
   }
+  // split form for kernels that fetch the row's operands before walking the row (k_bsr_spmv, U >= 4):
+  // row i of b, invd, d, xin is only ever written by row i's own epilogue, so the early read is safe
+  struct Pre {
+    double bi, invdi, di, xi;
+  };
+  __device__ Pre prefetch(int i) const { return Pre{b[i], invd[i], first ? 0.0 : d[i], xin[i]}; }
+  __device__ double finish(int i, double s, const Pre &p) const {
+    const double r = p.bi - s;
+    double dn = c2 * p.invdi * r;
+    if (!first) dn += c1 * p.di;
+    d[i] = dn;
+    const double xo = p.xi + dn;
+    xout[i] = xo;
+    return REDUCE ? p.bi * xo : 0.0;
+  }
+};
+// epilogues that offer the split prefetch / finish form (a nested Pre type)
+template <class Epi, class = void>
+struct EpiHasPrefetch {
+  static constexpr bool value = false;
+};
+template <class Epi>
+struct EpiHasPrefetch<Epi, std::void_t<typename Epi::Pre>> {
+  static constexpr bool value = true;
 };
 
 // ---- CSR SpMV, TPR threads per row, grid-stride over row chunks ----------------
@@ -283,11 +341,21 @@ struct BsrDev {
   int aos = 0;
 };
 
+struct NoPre {};
+template <class Epi, bool ON>
+struct PreOf {
+  using type = NoPre;
+};
+template <class Epi>
+struct PreOf<Epi, true> {
+  using type = typename Epi::Pre;
+};
 template <int B, int TPR, class Epi, bool TWO, bool AOS, int U = 1>
 __global__ void __launch_bounds__(kBlock) k_bsr_spmv(BsrDev A, XVec X, CsrDev C2, const double *__restrict__ t2, Epi epi,
                                                       Reducer R) {
   __shared__ double smem[32];
   constexpr int rows_per_block = kBlock / TPR;
+  constexpr bool kPre = U >= 4 && EpiHasPrefetch<Epi>::value && TPR >= B;
   const int lane = threadIdx.x & (TPR - 1);
   const int local_row = threadIdx.x / TPR;
   double contrib = 0.0;
@@ -307,6 +375,7 @@ __global__ void __launch_bounds__(kBlock) k_bsr_spmv(BsrDev A, XVec X, CsrDev C2
     double s[B];
 #pragma unroll
     for (int r = 0; r < B; ++r) s[r] = 0.0;
+    [[maybe_unused]] typename PreOf<Epi, kPre>::type pre{};
     if (I < A.nbrows) {
       int k0, k1;
       if constexpr (U >= 4) {
@@ -323,6 +392,8 @@ __global__ void __launch_bounds__(kBlock) k_bsr_spmv(BsrDev A, XVec X, CsrDev C2
       }
       const int nb = k1 - k0;
       const double *vb = A.v + (size_t)k0 * (B * B);
+      if constexpr (kPre)
+        if (lane < B) pre = epi.prefetch((int)(I * B + lane));
       for (int kk = lane; kk < nb; kk += U * TPR) {
         // U blocks per lane in flight: all loads of the U blocks are issued before any FMA
         double xj[U][B], a[U][B * B];
@@ -365,7 +436,10 @@ __global__ void __launch_bounds__(kBlock) k_bsr_spmv(BsrDev A, XVec X, CsrDev C2
 #pragma unroll
       for (int r = 1; r < B; ++r)
         if (lane == r) mine = s[r];
-      contrib += epi((int)(I * B + lane), mine);
+      if constexpr (kPre)
+        contrib += epi.finish((int)(I * B + lane), mine, pre);
+      else
+        contrib += epi((int)(I * B + lane), mine);
     }
   }
   if (Epi::kReduce) reduce_finalize(contrib, R, 0, 1, smem);
