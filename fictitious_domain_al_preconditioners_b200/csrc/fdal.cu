@@ -227,6 +227,7 @@ struct fdal_ctx {
   ncclComm_t comm = nullptr;
   int64_t n_dot_outer = 0;
   int stream_ctas_per_sm = 3, spmv_unroll = 4, bsr_unroll = 1;
+  bool spmv_prefetch = false;  // FDAL_SPMV_PF=1: k_spmv / k_spmv2 with next-row-pointer and epilogue-operand prefetch
   bool prefer_stream = false;
   int fail = 0;
   std::vector<void *> allocs;
@@ -565,7 +566,15 @@ static void spmv(fdal_ctx *c, const DevCsr &A, const double *x, Epi epi, double 
   const int g = grid_rows(c, A.d.nrows, A.d.tpr);
   Reducer R = reducer(c, red_out);
   XVec X = xv(A, x);
-  if (c->spmv_unroll > 1) {
+  if (c->spmv_prefetch) {
+    switch (A.d.tpr) {
+      case 2: k_spmv<2, Epi, 4, true><<<g, kBlock, 0, c->stream>>>(A.d, X, epi, R); break;
+      case 4: k_spmv<4, Epi, 4, true><<<g, kBlock, 0, c->stream>>>(A.d, X, epi, R); break;
+      case 8: k_spmv<8, Epi, 4, true><<<g, kBlock, 0, c->stream>>>(A.d, X, epi, R); break;
+      case 16: k_spmv<16, Epi, 4, true><<<g, kBlock, 0, c->stream>>>(A.d, X, epi, R); break;
+      default: k_spmv<32, Epi, 4, true><<<g, kBlock, 0, c->stream>>>(A.d, X, epi, R); break;
+    }
+  } else if (c->spmv_unroll > 1) {
     switch (A.d.tpr) {
       case 2: k_spmv<2, Epi, 4><<<g, kBlock, 0, c->stream>>>(A.d, X, epi, R); break;
       case 4: k_spmv<4, Epi, 4><<<g, kBlock, 0, c->stream>>>(A.d, X, epi, R); break;
@@ -607,7 +616,15 @@ static void spmv2(fdal_ctx *c, const DevCsr &A, const double *x, const DevCsr &C
   const int g = grid_rows(c, A.d.nrows, A.d.tpr);
   Reducer R = reducer(c, red_out);
   XVec X = xv(A, x);
-  if (c->spmv_unroll > 1) {
+  if (c->spmv_prefetch) {
+    switch (A.d.tpr) {
+      case 2: k_spmv2<2, Epi, 4, true><<<g, kBlock, 0, c->stream>>>(A.d, X, Ct.d, t, epi, R); break;
+      case 4: k_spmv2<4, Epi, 4, true><<<g, kBlock, 0, c->stream>>>(A.d, X, Ct.d, t, epi, R); break;
+      case 8: k_spmv2<8, Epi, 4, true><<<g, kBlock, 0, c->stream>>>(A.d, X, Ct.d, t, epi, R); break;
+      case 16: k_spmv2<16, Epi, 4, true><<<g, kBlock, 0, c->stream>>>(A.d, X, Ct.d, t, epi, R); break;
+      default: k_spmv2<32, Epi, 4, true><<<g, kBlock, 0, c->stream>>>(A.d, X, Ct.d, t, epi, R); break;
+    }
+  } else if (c->spmv_unroll > 1) {
     switch (A.d.tpr) {
       case 2: k_spmv2<2, Epi, 4><<<g, kBlock, 0, c->stream>>>(A.d, X, Ct.d, t, epi, R); break;
       case 4: k_spmv2<4, Epi, 4><<<g, kBlock, 0, c->stream>>>(A.d, X, Ct.d, t, epi, R); break;
@@ -1642,6 +1659,7 @@ int fdal_create(fdal_ctx **out, const fdal_config *cfg) {
   if (const char *e = getenv("FDAL_SPMV")) c->prefer_stream = strcmp(e, "stream") == 0;
   if (const char *e = getenv("FDAL_UNROLL")) c->spmv_unroll = atoi(e);
   if (const char *e = getenv("FDAL_BSR_UNROLL")) c->bsr_unroll = atoi(e);
+  if (const char *e = getenv("FDAL_SPMV_PF")) c->spmv_prefetch = atoi(e) > 0;
   if (const char *e = getenv("FDAL_STREAM_CTAS")) c->stream_ctas_per_sm = std::max(1, atoi(e));
   *out = c;
   return FDAL_OK;

@@ -241,6 +241,15 @@ template <class Epi>
 struct EpiHasPrefetch<Epi, std::void_t<typename Epi::Pre>> {
   static constexpr bool value = true;
 };
+struct NoPre {};
+template <class Epi, bool ON>
+struct PreOf {
+  using type = NoPre;
+};
+template <class Epi>
+struct PreOf<Epi, true> {
+  using type = typename Epi::Pre;
+};
 
 // ---- CSR SpMV, TPR threads per row, grid-stride over row chunks ----------------
 // row-group partial sum with U independent (value, column, x) load chains in flight per
@@ -273,24 +282,56 @@ __device__ __forceinline__ double row_partial(const CsrDev &A, const XVec &X, in
   return s;
 }
 
-template <int TPR, class Epi, int U = 1>
+// PF (opt-in, FDAL_SPMV_PF=1): the row pointers of the next grid-stride step and the epilogue's row
+// operands are fetched before the row is walked: rp -> (ci,v) -> x -> epilogue loads -> stores
+// becomes (ci,v) -> x -> stores.
+template <int TPR, class Epi, int U = 1, bool PF = false>
 __global__ void __launch_bounds__(kBlock) k_spmv(CsrDev A, XVec X, Epi epi, Reducer R) {
   __shared__ double smem[32];
   constexpr int rows_per_block = kBlock / TPR;
+  constexpr bool kPre = PF && EpiHasPrefetch<Epi>::value;
   const int lane = threadIdx.x & (TPR - 1);
   const int local_row = threadIdx.x / TPR;
   double contrib = 0.0;
+  int k0n = 0, k1n = 0;
+  if constexpr (PF) {
+    const long long row0 = (long long)blockIdx.x * rows_per_block + local_row;
+    if (row0 < A.nrows) {
+      k0n = __ldg(A.rp + row0);
+      k1n = __ldg(A.rp + row0 + 1);
+    }
+  }
   for (long long base = (long long)blockIdx.x * rows_per_block; base < A.nrows;
        base += (long long)gridDim.x * rows_per_block) {
     const long long row = base + local_row;
     double s = 0.0;
+    [[maybe_unused]] typename PreOf<Epi, kPre>::type pre{};
     if (row < A.nrows) {
-      const int k0 = __ldg(A.rp + row), k1 = __ldg(A.rp + row + 1);
+      int k0, k1;
+      if constexpr (PF) {
+        k0 = k0n;
+        k1 = k1n;
+        const long long rown = row + (long long)gridDim.x * rows_per_block;
+        if (rown < A.nrows) {
+          k0n = __ldg(A.rp + rown);
+          k1n = __ldg(A.rp + rown + 1);
+        }
+      } else {
+        k0 = __ldg(A.rp + row);
+        k1 = __ldg(A.rp + row + 1);
+      }
+      if constexpr (kPre)
+        if (lane == 0) pre = epi.prefetch((int)row);
       s = row_partial<TPR, U>(A, X, k0, k1, lane);
     }
 #pragma unroll
     for (int o = TPR >> 1; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, TPR);
-    if (lane == 0 && row < A.nrows) contrib += epi((int)row, s);
+    if (lane == 0 && row < A.nrows) {
+      if constexpr (kPre)
+        contrib += epi.finish((int)row, s, pre);
+      else
+        contrib += epi((int)row, s);
+    }
   }
   if (Epi::kReduce) reduce_finalize(contrib, R, 0, 1, smem);
 }
@@ -299,27 +340,63 @@ __global__ void __launch_bounds__(kBlock) k_spmv(CsrDev A, XVec X, Epi epi, Redu
 // Two CSR matrices with the same row partition are walked in one row pass, so A x
 // never goes to memory before the coupling term is added (K3).  t already carries
 // gamma * W^-1 C x (phase 1), and for the block system also + x1.
-template <int TPR, class Epi, int U = 1>
+template <int TPR, class Epi, int U = 1, bool PF = false>
 __global__ void __launch_bounds__(kBlock) k_spmv2(CsrDev A, XVec X, CsrDev Ct, const double *__restrict__ t, Epi epi,
                                                    Reducer R) {
   __shared__ double smem[32];
   constexpr int rows_per_block = kBlock / TPR;
+  constexpr bool kPre = PF && EpiHasPrefetch<Epi>::value;
   const int lane = threadIdx.x & (TPR - 1);
   const int local_row = threadIdx.x / TPR;
   double contrib = 0.0;
+  int k0n = 0, k1n = 0, c0n = 0, c1n = 0;
+  if constexpr (PF) {
+    const long long row0 = (long long)blockIdx.x * rows_per_block + local_row;
+    if (row0 < A.nrows) {
+      k0n = __ldg(A.rp + row0);
+      k1n = __ldg(A.rp + row0 + 1);
+      c0n = __ldg(Ct.rp + row0);
+      c1n = __ldg(Ct.rp + row0 + 1);
+    }
+  }
   for (long long base = (long long)blockIdx.x * rows_per_block; base < A.nrows;
        base += (long long)gridDim.x * rows_per_block) {
     const long long row = base + local_row;
     double s = 0.0;
+    [[maybe_unused]] typename PreOf<Epi, kPre>::type pre{};
     if (row < A.nrows) {
-      const int k0 = __ldg(A.rp + row), k1 = __ldg(A.rp + row + 1);
-      const int c0 = __ldg(Ct.rp + row), c1 = __ldg(Ct.rp + row + 1);
+      int k0, k1, c0, c1;
+      if constexpr (PF) {
+        k0 = k0n;
+        k1 = k1n;
+        c0 = c0n;
+        c1 = c1n;
+        const long long rown = row + (long long)gridDim.x * rows_per_block;
+        if (rown < A.nrows) {
+          k0n = __ldg(A.rp + rown);
+          k1n = __ldg(A.rp + rown + 1);
+          c0n = __ldg(Ct.rp + rown);
+          c1n = __ldg(Ct.rp + rown + 1);
+        }
+      } else {
+        k0 = __ldg(A.rp + row);
+        k1 = __ldg(A.rp + row + 1);
+        c0 = __ldg(Ct.rp + row);
+        c1 = __ldg(Ct.rp + row + 1);
+      }
+      if constexpr (kPre)
+        if (lane == 0) pre = epi.prefetch((int)row);
       s = row_partial<TPR, U>(A, X, k0, k1, lane);
       for (int k = c0 + lane; k < c1; k += TPR) s += __ldg(Ct.v + k) * __ldg(t + __ldg(Ct.ci + k));
     }
 #pragma unroll
     for (int o = TPR >> 1; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, TPR);
-    if (lane == 0 && row < A.nrows) contrib += epi((int)row, s);
+    if (lane == 0 && row < A.nrows) {
+      if constexpr (kPre)
+        contrib += epi.finish((int)row, s, pre);
+      else
+        contrib += epi((int)row, s);
+    }
   }
   if (Epi::kReduce) reduce_finalize(contrib, R, 0, 1, smem);
 }
@@ -341,15 +418,6 @@ struct BsrDev {
   int aos = 0;
 };
 
-struct NoPre {};
-template <class Epi, bool ON>
-struct PreOf {
-  using type = NoPre;
-};
-template <class Epi>
-struct PreOf<Epi, true> {
-  using type = typename Epi::Pre;
-};
 template <int B, int TPR, class Epi, bool TWO, bool AOS, int U = 1>
 __global__ void __launch_bounds__(kBlock) k_bsr_spmv(BsrDev A, XVec X, CsrDev C2, const double *__restrict__ t2, Epi epi,
                                                       Reducer R) {

@@ -23,7 +23,7 @@ configs = [c.split(",") for c in os.environ.get("PROBE_CONFIGS", "").split(";") 
     ["FDAL_SPMV=stream", "FDAL_STREAM_CTAS=3"],
     ["FDAL_SPMV=stream", "FDAL_STREAM_CTAS=2"],
 ]
-KN = ("FDAL_SPMV", "FDAL_UNROLL", "FDAL_TPR", "FDAL_STREAM_CTAS", "FDAL_NO_BSR", "FDAL_BSR_TPR", "FDAL_BSR_AOS", "FDAL_BSR_UNROLL")
+KN = ("FDAL_SPMV", "FDAL_UNROLL", "FDAL_TPR", "FDAL_STREAM_CTAS", "FDAL_NO_BSR", "FDAL_BSR_TPR", "FDAL_BSR_AOS", "FDAL_BSR_UNROLL", "FDAL_SPMV_PF", "FDAL_DENSE_WINV")
 lp = part.distribute_problem(prob, H, 0, 1)
 prob.config.block_size = lp.block_size
 print(f"workload {wname} N={prob.n_dofs} nnz(A)={prob.A.nnz} levels={H[0].describe()}")
