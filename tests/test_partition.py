@@ -304,3 +304,52 @@ def test_inconsistent_halo_plans_are_refused_on_the_host():
     sigs[1][("mat", b.MAT_A)][0][0] += 1
     with pytest.raises(ValueError, match="halo plan mismatch"):
         part.check_plan_signatures(sigs)
+
+
+def _emulated_spmv(A, row_off, col_off, x, col_bs):
+    """What the ranks compute together: pack -> exchange (by the plans) -> local SpMV on [owned | halo]."""
+    nranks = len(row_off) - 1
+    part.clear_cache()
+    dcs = [part.localize(A, row_off, col_off, r, col_bs) for r in range(nranks)]
+    part.clear_cache()
+    owned = [x[col_off[r]: col_off[r + 1]] for r in range(nranks)]
+    out = []
+    for r in range(nranks):
+        pl = dcs[r].plan
+        halo = []
+        for q in range(nranks):  # halo entries are ordered by owner rank
+            so = np.concatenate([[0], np.cumsum(dcs[q].plan.send_counts)])
+            sent = owned[q][dcs[q].plan.send_idx[so[r]: so[r + 1]]]
+            assert sent.size == pl.recv_counts[q]
+            halo.append(sent)
+        xl = np.concatenate([owned[r]] + halo)
+        assert xl.size == dcs[r].local.shape[1] == pl.n_owned + pl.n_halo
+        out.append(dcs[r].local @ xl)
+    return np.concatenate(out)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_matrices_through_emulated_halo_exchange(seed):
+    """Random sparse (also rectangular) matrices, random rank counts including ranks that own no rows
+    or no columns, scalar and node-interleaved column spaces: the plans reproduce the global product."""
+    rng = np.random.default_rng(seed)
+    bs = int(rng.choice([1, 1, 2, 3]))
+    nranks = int(rng.integers(2, 7))
+    nr = int(rng.integers(1, 40)) * bs
+    nc = int(rng.integers(1, 40)) * bs
+    A = sp.random(nr, nc, density=float(rng.uniform(0.02, 0.4)), random_state=seed, format="csr")
+    x = rng.uniform(-1, 1, nc)
+
+    def offsets(n):  # random cuts on node boundaries, empty shares allowed
+        cuts = np.sort(rng.integers(0, n // bs + 1, nranks - 1)) * bs
+        return np.concatenate([[0], cuts, [n]]).astype(np.int64)
+
+    row_off, col_off = offsets(nr), offsets(nc)
+    y = _emulated_spmv(A, row_off, col_off, x, bs)
+    assert np.allclose(y, A @ x, rtol=0, atol=1e-13)
+    if bs > 1:  # halos hold whole nodes
+        part.clear_cache()
+        for r in range(nranks):
+            hg = part.localize(A, row_off, col_off, r, bs).plan.halo_globals
+            assert hg.size % bs == 0 and np.array_equal(hg.reshape(-1, bs)[:, 0] % bs, np.zeros(hg.size // bs))
+        part.clear_cache()
