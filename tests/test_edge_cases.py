@@ -17,7 +17,9 @@ def _make(kind, oracle_mod, cfg):
     return oracle_mod.OracleContext(cfg) if kind == "oracle" else ALContext(cfg)
 
 
-KINDS = ["oracle", pytest.param("cuda", marks=pytest.mark.gpu)]
+# the CUDA leg was written after the last GPU run of round 1: non-strict xfail until it has been seen green once
+KINDS = ["oracle", pytest.param("cuda", marks=[pytest.mark.gpu, pytest.mark.xfail(
+    strict=False, reason="CUDA leg not yet run on a GPU (written after the last GPU call of round 1)")])]
 
 
 def _raw_set_csr(ctx, mid, nr, nc, rp, ci, v):
