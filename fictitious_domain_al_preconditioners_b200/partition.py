@@ -376,6 +376,8 @@ def plan_signature(lp: LocalProblem) -> dict:
         if dc.plan is not None:
             sig[("mat", mid)] = (dc.plan.send_counts.copy(), dc.plan.recv_counts.copy())
     for which, LH in lp.amg.items():
+        if not isinstance(LH, LocalHierarchy):
+            continue  # replicated hierarchy of an immersed block: no exchange
         for l, L in enumerate(LH.levels):
             for tag, dc in (("A", L.A), ("P", L.P), ("R", L.R)):
                 if dc is not None and dc.plan is not None:

@@ -304,6 +304,10 @@ def test_inconsistent_halo_plans_are_refused_on_the_host():
     sigs[1][("mat", b.MAT_A)][0][0] += 1
     with pytest.raises(ValueError, match="halo plan mismatch"):
         part.check_plan_signatures(sigs)
+    # problems with a replicated immersed-block hierarchy (elliptic kinds) pass through the check too
+    prob = syn.elliptic_interface(cycle=1)
+    lps = part.distribute_all(prob, syn.build_hierarchies(prob, max_coarse=40), 2)
+    assert not isinstance(lps[0].amg[b.AMG_A22], part.LocalHierarchy) and part.plan_signature(lps[0])
 
 
 def _emulated_spmv(A, row_off, col_off, x, col_bs):
