@@ -1,14 +1,18 @@
 #!/usr/bin/env python
 """bench.py — outer FGMRES solve time / DoFs/s of the AL solve path on B200.
 
-One "step" = one complete outer solve (FGMRES right-preconditioned by the
-block-triangular AL preconditioner, inner PCG + AMG V-cycle) of the synthetic
-refinement of the named parameter file.  Prints ONE JSON line (see the contract in
-DESIGN.md "Measurement").
+One "step" = one complete outer solve (FGMRES right-preconditioned by the block-triangular AL
+preconditioner, inner PCG + AMG V-cycle) of the synthetic refinement of the named parameter file.
+Prints ONE JSON line (contract: DESIGN.md "Measurement").
 
-  python bench.py                       # N=1, default workload, few steps
-  python bench.py --impl reference      # the CPU restatement (oracle) on host cores
-  torchrun ... bench.py --gpus N ...    # one rank per GPU (row-partitioned solve)
+  python bench.py                       # N=1, headline workload (3-D Stokes IB, 10.35 M DoFs)
+  python bench.py --impl reference      # the CPU restatement (oracle): ONE COMPLETE solve, all host cores
+  torchrun ... bench.py --gpus N ...    # the SAME problem row-partitioned over N GPUs (strong scaling)
+
+Every timed step goes through the reference-facing C-ABI call `fdal_solve` with pinned HOST buffers
+(H2D of right-hand side and initial guess, D2H of the solution inside the timed wall-clock region =
+`e2e`); the CUDA events inside the same call bracket the device-resident part (inputs already in
+HBM) = `value`.
 """
 from __future__ import annotations
 
@@ -43,22 +47,41 @@ def emit(line: str):
     os.write(_RESULT_FD if _RESULT_FD is not None else 1, (line + "\n").encode())
 
 
+def log(msg):
+    sys.stderr.write(f"[bench {time.strftime('%H:%M:%S')}] {msg}\n")
+    sys.stderr.flush()
+
+
 METRIC = "outer_fgmres_solve_dofs_per_s"
 UNIT = "DoF/s"
+DEFAULT_WORKLOAD = "stokes3d_10M"
 
 WORKLOADS = {
-    # configs[1]: stokes_immersed_boundary 2D, parameters_stokes.prm as shipped, ~1M DoFs
-    "stokes2d_1M": dict(kind="stokes", dim=2, nel=320, diagonal_mass=False,
-                        label="stokes_immersed_boundary 2D parameters_stokes.prm (exact mass inverses), Q2^2-Q1 nel=320"),
-    # configs[3] family: stokes_immersed_boundary 3D, parameters_stokes_3d.prm (diagonal W^-1, lumped-CG Mp^-1)
+    # configs[3] (headline, north_star): stokes_immersed_boundary 3D, parameters_stokes_3d.prm (diagonal W^-1,
+    # lumped-CG Mp^-1), Q2^3-Q1 on 74^3 cells = 10.35 M DoFs; row-partitioned over 1/2/4/8 GPUs
+    "stokes3d_10M": dict(kind="stokes", dim=3, nel=74, diagonal_mass=True,
+                         label="stokes_immersed_boundary 3D parameters_stokes_3d.prm, Q2^3-Q1 nel=74"),
     "stokes3d": dict(kind="stokes", dim=3, nel=32, diagonal_mass=True,
                      label="stokes_immersed_boundary 3D parameters_stokes_3d.prm, Q2^3-Q1 nel=32"),
+    # configs[1]: stokes_immersed_boundary 2D, parameters_stokes.prm as shipped (exact mass inverses), ~1M DoFs
+    "stokes2d_1M": dict(kind="stokes", dim=2, nel=320, diagonal_mass=False,
+                        label="stokes_immersed_boundary 2D parameters_stokes.prm (exact mass inverses), Q2^2-Q1 nel=320"),
     "stokes2d_diag": dict(kind="stokes", dim=2, nel=320, diagonal_mass=True,
                           label="stokes_immersed_boundary 2D, diagonal mass, Q2^2-Q1 nel=320"),
-    "laplace": dict(kind="laplace", r_bg=10, label="immersed_laplace 2D circle, Q1 r=10"),
+    # configs[0]: immersed_laplace 2D circle as shipped (Circle_parameters_f1_g1 family: matrix-free
+    # K + gamma Ct (M^-1 M^-1) C with exact mass inverses, immersed_laplace.cc:875-884)
+    "laplace": dict(kind="laplace", r_bg=10, diagonal_inverse=False,
+                    label="immersed_laplace 2D circle, exact (M^-1)^2 as shipped, Q1 r=10"),
+    "laplace_diag": dict(kind="laplace", r_bg=10, diagonal_inverse=True,
+                         label="immersed_laplace 2D circle, diagonal W^-1, Q1 r=10"),
+    # configs[2]: elliptic_interface co-dim 0, parameters_ideal.prm (modified AL, h-scaled mass, exact M^-1),
+    # --beta2 sweeps the coefficient jump, --cycle the refinement (cycle 7 = 4.2 M background DoFs)
+    "elliptic": dict(kind="elliptic", cycle=6, beta2=1e3,
+                     label="elliptic_interface parameters_ideal.prm (modified AL), cycle=6"),
     # configs[4] family: elasticity.prm (vector-valued elliptic interface, BSR-3 path)
     "elasticity": dict(kind="elasticity", dim=3, nel=64, label="elliptic_interface elasticity.prm, Q1^3 vector nel=64"),
-    "tiny": dict(kind="stokes", dim=2, nel=32, diagonal_mass=True, label="tiny smoke workload"),
+    "tiny": dict(kind="stokes", dim=2, nel=32, diagonal_mass=True, label="tiny smoke workload, Q2^2-Q1 nel=32"),
+    "tiny3d": dict(kind="stokes", dim=3, nel=8, diagonal_mass=True, label="tiny 3-D smoke workload, Q2^3-Q1 nel=8"),
 }
 
 
@@ -71,10 +94,18 @@ def build_problem(w):
                                             numbering="node")
     elif w["kind"] == "elasticity":
         prob = syn.elasticity_interface(nel_bg=w["nel"], nel_imm=max(2, w["nel"] // 4), diagonal_inverse=True)
+    elif w["kind"] == "elliptic":
+        prob = syn.elliptic_interface(cycle=w["cycle"], beta2=w.get("beta2", 1e3))
     else:
-        prob = syn.immersed_laplace(r_bg=w["r_bg"], diagonal_inverse=True)
+        prob = syn.immersed_laplace(r_bg=w["r_bg"], diagonal_inverse=w.get("diagonal_inverse", False))
     H = syn.build_hierarchies(prob)
     return prob, H
+
+
+def config_of(wname, w, n_dofs, world, scaling):
+    """The keys BOTH arms print (identical for the same job)."""
+    return {"workload": wname, "description": w["label"], "n_dofs": int(n_dofs), "n_gpus_job": int(world),
+            "scaling_mode": scaling}
 
 
 class ClockSampler(threading.Thread):
@@ -112,7 +143,7 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.samples)}
 
 
-def measured_peak():
+def measured_peak(sustained=False):
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         try:
@@ -122,149 +153,159 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def cpu_sample(prob, H, threads, outer_steps=2):
-    """Time the oracle on host cores on a bounded sample: the first `outer_steps` outer
-    iterations of the SAME solve, extrapolated with the full iteration count."""
-    import copy
-
-    from fictitious_domain_al_preconditioners_b200 import synthetic as syn
-    from oracle import oracle
-
-    cfg = copy.deepcopy(prob.config)
-    cfg.outer.max_steps = outer_steps
-    p2 = copy.copy(prob)
-    p2.config = cfg
-    ctx = syn.setup_context(oracle.OracleContext(cfg, threads=threads), p2, H, oracle=True)
-    rhs = ctx.augment_rhs(prob.rhs) if prob.augment_rhs else prob.rhs
-    t0 = time.perf_counter()
-    _, info = ctx.solve(rhs, raise_on_failure=False)
-    dt = time.perf_counter() - t0
-    its = max(1, info.outer_iterations)
-    ctx.close()
-    return dt / its, its  # seconds per outer iteration
+def weak_scaled(w, world):
+    if world <= 1 or "nel" not in w:
+        return w
+    w = dict(w)
+    w["nel"] = int(round(w["nel"] * world ** (1.0 / w["dim"]) / 2.0)) * 2
+    w["label"] = w["label"].rsplit("nel=", 1)[0] + f"nel={w['nel']} (weak-scaled x{world})"
+    return w
 
 
-CPU_SAMPLE_MAX_DOFS = 1_500_000
-
-
-def bounded_cpu_problem(w, prob, H):
-    """The CPU arm must finish in minutes: beyond ~1.5 M DoFs the oracle is timed on a coarser
-    refinement of the same parameter file (CPU DoF/s does not improve with size, so this
-    does not flatter the GPU)."""
-    if prob.n_dofs <= CPU_SAMPLE_MAX_DOFS or "nel" not in w:
-        return prob, H, "the same solve"
-    w2 = dict(w)
-    dim = w.get("dim", 2)
-    w2["nel"] = max(8, int(w["nel"] * (1.0e6 / prob.n_dofs) ** (1.0 / dim) / 2) * 2)
-    sprob, sH = build_problem(w2)
-    return sprob, sH, f"the same parameter file at nel={w2['nel']} ({sprob.n_dofs} DoFs)"
-
-
-def estimate_dofs(w):
-    """DoFs of a Stokes workload without building it (the reference arm only needs the count)."""
-    if w.get("kind") != "stokes":
-        return None
-    dim, nel = w["dim"], w["nel"]
-    if dim == 2:
-        m = 2 * (2 ** int(round(np.log2(nel))) + 1)
-    else:
-        k = max(1, int(round(np.log2(nel))) - 3)
-        m = 3 * (6 * 4**k + 2)
-    return dim * (2 * nel + 1) ** dim + (nel + 1) ** dim + m
-
-
+# --------------------------------------------------------------------------------------- reference arm
 def run_reference(args, w, wname):
-    """--impl reference: the reference's CPU path.  The reference binary cannot be
-    built here (deal.II / Trilinos / UMFPACK absent), so this times the oracle port
-    with all host threads, on a bounded sample of the same workload."""
+    """--impl reference: the reference's CPU path.  The reference binary cannot be built here
+    (deal.II / Trilinos / UMFPACK absent), so this times the oracle port with all host
+    threads.  A step is ONE COMPLETE outer solve of the benched problem — measured, nothing
+    extrapolated.  The run stops early once FDAL_REF_BUDGET_S (default 600 s) of solving has been
+    spent (always at least one complete solve); `steps` / `warmup` report what was actually run."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from fictitious_domain_al_preconditioners_b200 import synthetic as syn
     from oracle import oracle
 
     api = oracle.load()
     cores = max(1, min(api.get_max_threads(), os.cpu_count() or 1))
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     world = max(1, args.gpus)
-    if world > 1 and "nel" in w:  # the same weak-scaled job as our arm at this GPU count
-        w = dict(w)
-        w["nel"] = int(round(w["nel"] * world ** (1.0 / w["dim"]) / 2.0)) * 2
-        w["label"] = w["label"].rsplit("nel=", 1)[0] + f"nel={w['nel']} (weak-scaled x{world})"
-    n_est = estimate_dofs(w)
-    if n_est is not None and n_est > CPU_SAMPLE_MAX_DOFS:
-        # do not assemble the big problem just to count its unknowns
-        w2 = dict(w)
-        w2["nel"] = max(8, int(w["nel"] * (1.0e6 / n_est) ** (1.0 / w["dim"]) / 2) * 2)
-        prob, H = build_problem(w2)
-        n_full = n_est
-        note = f"the same parameter file at nel={w2['nel']} ({prob.n_dofs} DoFs)"
-    else:
-        prob, H = build_problem(w)
-        n_full = prob.n_dofs
-        prob, H, note = bounded_cpu_problem(w, prob, H)
-    sample_outer = 2
-    vals = []
-    for i in range(args.warmup + args.steps):
-        per_it, _ = cpu_sample(prob, H, cores, sample_outer)
-        if i >= args.warmup:
-            vals.append(per_it)
-    per_it = float(np.mean(vals))
-    n_outer = args.expected_outer or estimate_outer(w)
-    t_solve = per_it * n_outer
+    if args.scaling == "weak":
+        w = weak_scaled(w, world)
+    t0 = time.perf_counter()
+    prob, H = build_problem(w)
+    t_setup = time.perf_counter() - t0
+    log(f"reference arm: problem + hierarchy in {t_setup:.1f} s, {prob.n_dofs} DoFs")
+    ctx = syn.setup_context(oracle.OracleContext(prob.config, threads=cores), prob, H, oracle=True)
+    rhs = ctx.augment_rhs(prob.rhs) if prob.augment_rhs else prob.rhs
+    budget = float(os.environ.get("FDAL_REF_BUDGET_S", "600"))
+    times, infos, spent, n_warm = [], [], 0.0, 0
+    want_warm = args.warmup
+    while len(times) < max(1, args.steps):
+        t0 = time.perf_counter()
+        _, info = ctx.solve(rhs, raise_on_failure=False)
+        dt = time.perf_counter() - t0
+        spent += dt
+        log(f"reference arm: complete solve in {dt:.2f} s ({info.outer_iterations} outer / {info.inner_iterations} inner)")
+        # a warm-up solve is only affordable when a solve is short compared with the budget
+        if n_warm < want_warm and spent + dt * (1 + len(times)) < budget * 0.5:
+            n_warm += 1
+            continue
+        times.append(dt)
+        infos.append(info)
+        if spent + dt > budget:
+            break
+    ctx.close()
+    t_solve = float(np.mean(times))
     value = prob.n_dofs / t_solve
+    info = infos[-1]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": n_full / value * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wname, "description": w["label"], "n_dofs": n_full},
+        "steps": len(times), "warmup": n_warm, "requested": {"steps": args.steps, "warmup": args.warmup},
+        "ms_per_step": t_solve * 1e3, "higher_is_better": True,
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_of(wname, w, prob.n_dofs, world, args.scaling),
+        "solve": {"outer_iterations": int(info.outer_iterations), "inner_iterations": int(info.inner_iterations),
+                  "final_residual": info.final_residual, "status": int(info.status), "setup_s": t_setup,
+                  "solve_s_each": times},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"first {sample_outer} outer FGMRES iterations of {note} on {cores} OpenMP threads, "
-                                   f"extrapolated to {n_outer} outer iterations", "n_dofs_sample": prob.n_dofs},
+                         "sample": f"{len(times)} COMPLETE outer solve(s) of the benched problem ({prob.n_dofs} DoFs) by the "
+                                   f"oracle port on {cores} OpenMP threads after {n_warm} warm-up solve(s); measured, not "
+                                   f"extrapolated; run bounded by a {budget:.0f} s solve budget"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(json.dumps(line))
 
 
-_OUTER_CACHE = {}
+# --------------------------------------------------------------------------------------- CPU-side checks
+def scipy_apply_system(prob, x):
+    """AA x of the Stokes / Laplace block system straight from the scipy blocks (independent of the
+    oracle and of the CUDA library): the N>1 parity check of the partitioned operator."""
+    from fictitious_domain_al_preconditioners_b200 import _binding as b
+
+    kind = prob.config.kind
+    n, m = prob.Ct.shape
+    g = prob.config.gamma
+    x0 = x[:n]
+    cx = prob.Ct.T @ x0
+    if prob.config.winv_mode != b.WINV_DIAG or prob.config.aug_explicit:
+        return None
+    t = g * prob.winv_diag * cx
+    if kind == b.KIND_LAPLACE:
+        return np.concatenate([prob.A @ x0 + prob.Ct @ (t + x[n:]), cx])
+    if kind in (b.KIND_STOKES, b.KIND_STOKES_DIAG_MINRES) and not prob.config.grad_div_in_operator:
+        n_p = prob.Bt.shape[1]
+        x1, x2 = x[n:n + n_p], x[n + n_p:]
+        return np.concatenate([prob.A @ x0 + prob.Ct @ (t + x2) + prob.Bt @ x1, prob.Bt.T @ x0, cx])
+    return None
 
 
-def estimate_outer(w):
-    """Outer iteration count of the workload (mesh independent): taken from a coarse
-    refinement of the same parameter file solved by the oracle."""
-    key = json.dumps(w, sort_keys=True)
-    if key in _OUTER_CACHE:
-        return _OUTER_CACHE[key]
+def oracle_checks(prob, H, ctx_gpu, lp, x_solution, rhs, n_inner, threads_all):
+    """N=1: parity of one block-system apply and one V-cycle against the oracle at the benched size,
+    the true residual of the GPU solution, and the bounded CPU sample (one inner PCG iteration's
+    work — V-cycle + augmented apply — on 1 thread and on all threads)."""
     from fictitious_domain_al_preconditioners_b200 import synthetic as syn
     from oracle import oracle
 
-    w2 = dict(w)
-    if w["kind"] == "elasticity":
-        w2["nel"] = 16
-    elif w["kind"] == "stokes":
-        w2["nel"] = 32 if w["dim"] == 2 else 8
-    else:
-        w2["r_bg"] = 6
-    prob, H = build_problem(w2)
-    ctx = syn.setup_context(oracle.OracleContext(prob.config), prob, H, oracle=True)
-    rhs = ctx.augment_rhs(prob.rhs) if prob.augment_rhs else prob.rhs
-    _, info = ctx.solve(rhs, raise_on_failure=False)
-    _OUTER_CACHE[key] = max(1, info.outer_iterations)
-    return _OUTER_CACHE[key]
+    t0 = time.perf_counter()
+    ora = syn.setup_context(oracle.OracleContext(prob.config, threads=threads_all), prob, H, oracle=True)
+    log(f"oracle context for the parity object / CPU sample: {time.perf_counter() - t0:.1f} s")
+    rng = np.random.default_rng(0)
+    N, n0 = prob.n_dofs, prob.sizes[0]
+    x = rng.uniform(-1, 1, N)
+    r = rng.uniform(-1, 1, n0)
+
+    def rel(a, ref):
+        return float(np.linalg.norm(a - ref) / max(np.linalg.norm(ref), 1e-300))
+
+    par = {}
+    yo = ora.apply_system(x)
+    par["apply_system_vs_oracle"] = rel(lp.gather([ctx_gpu.apply_system(lp.scatter(x))]), yo)
+    xs = np.concatenate([r, np.zeros(N - n0)])
+    zg = ctx_gpu.apply_amg(lp.scatter(xs)[:n0])
+    zo = ora.apply_amg(r)
+    par["apply_amg_vs_oracle"] = rel(lp.gather([np.concatenate([zg, np.zeros(N - n0)])])[:n0], zo)
+    ao = ora.apply_aug(r)
+    ag = ctx_gpu.apply_aug(lp.scatter(xs)[:n0])
+    par["apply_aug_vs_oracle"] = rel(lp.gather([np.concatenate([ag, np.zeros(N - n0)])])[:n0], ao)
+    xg = lp.gather([x_solution])
+    rhs_g = lp.gather([rhs])
+    par["true_residual_rel"] = rel(ora.apply_system(xg), rhs_g)
+    par["n_dofs"] = int(N)
+    par["tolerances"] = {"apply": 1e-12, "solution": 1e-10}
+    # bounded CPU sample
+    sample = {}
+    for thr in (1, threads_all):
+        oracle.load().set_num_threads(thr)
+        reps = 1 if thr == 1 else 3
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            ora.apply_amg(r)
+            ora.apply_aug(r)
+        sample[thr] = (time.perf_counter() - t0) / reps
+    ora.close()
+    return par, sample
 
 
+# --------------------------------------------------------------------------------------- our arm
 def run_ours(args, w, wname):
     world_env = int(os.environ.get("WORLD_SIZE", "1"))
     # torchrun pins OMP_NUM_THREADS=1; the host-side setup helpers (OpenMP SpGEMM, BSR
     # conversion) should share the box's cores between the ranks instead
     os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // max(1, world_env)))
-    if world_env > 1:
-        # every rank builds the hierarchy itself: keep the setup bit-reproducible across ranks
-        # (no GPU mat-vec in the eigenvalue estimate) so all ranks cut identical matrices
-        os.environ["FDAL_DETERMINISTIC_SETUP"] = "1"
     import torch
 
     from fictitious_domain_al_preconditioners_b200 import ALContext
     from fictitious_domain_al_preconditioners_b200 import _binding as b
-    from fictitious_domain_al_preconditioners_b200 import synthetic as syn
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -272,7 +313,7 @@ def run_ours(args, w, wname):
     if world > 1:
         import torch.distributed as dist
 
-        # a rank that fails leaves the others inside an NCCL call for ever: bound the damage
+        # a rank that fails leaves the others inside a spinning kernel for ever: bound the damage
         limit = float(os.environ.get("FDAL_BENCH_WATCHDOG_S", "1500"))
 
         def _bail():
@@ -287,22 +328,22 @@ def run_ours(args, w, wname):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     t0 = time.perf_counter()
-    if world > 1 and "nel" in w:
-        # weak scaling: per-GPU work fixed, the global grid grows with the GPU count
-        w = dict(w)
-        w["nel"] = int(round(w["nel"] * world ** (1.0 / w["dim"]) / 2.0)) * 2
-        w["label"] = w["label"].rsplit("nel=", 1)[0] + f"nel={w['nel']} (weak-scaled x{world})"
+    if args.scaling == "weak":
+        w = weak_scaled(w, world)
     from fictitious_domain_al_preconditioners_b200 import partition as part
 
     prob = H = None
+    keep = {}
 
     def build():
         p_, H_ = build_problem(w)
         meta = dict(n_dofs=int(p_.n_dofs), sizes=[int(x) for x in p_.sizes], nnz_A=int(p_.A.nnz),
                     amg_levels=H_[0].describe())
+        keep["prob"] = p_  # rank 0 keeps the global blocks for the N>1 parity check
         return p_, H_, meta
 
     uid = [bytes(128)]
+    gloo = None
     if world > 1:
         import torch.distributed as dist
 
@@ -315,11 +356,13 @@ def run_ours(args, w, wname):
         amg_setup.set_host_threads(ncpu if rank == 0 else 1)  # rank 0 sets up with the whole box
         lp = part.share_local_problems(build, rank, world, gloo)
         amg_setup.set_host_threads(max(1, ncpu // world))  # then every rank gets its share
+        prob = keep.get("prob")
     else:
         prob, H, meta = build()
         lp = part.distribute_problem(prob, H, 0, 1)
         lp.rhs_local, lp.augment_rhs, lp.meta = lp.scatter(prob.rhs), bool(prob.augment_rhs), meta
     t_gen = time.perf_counter() - t0
+    log(f"rank {rank}: problem + hierarchy + partition in {t_gen:.1f} s")
     cfg = lp.config
     cfg.device = local_rank
     cfg.use_graphs = not args.no_graphs
@@ -331,75 +374,65 @@ def run_ours(args, w, wname):
         uid = [ctx.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0, group=gloo)
     part.setup_local_context(ctx, lp, uid[0])
+    comm_mode = {0: "single GPU", 1: "nccl send/recv + all-reduce", 2: "peer channels (cudaIpc, in-kernel NVLink stores)"}[
+        ctx.api.comm_mode(ctx._h)]
     rhs = lp.rhs_local
     if lp.augment_rhs:
         rhs = ctx.augment_rhs(rhs)
     N = rhs.size
     n_dofs_global = lp.meta["n_dofs"]
     t_setup = time.perf_counter() - t0
+    log(f"rank {rank}: upload + finalize in {t_setup:.1f} s ({comm_mode})")
 
     def barrier():
         if world > 1:
-            import torch.distributed as dist
-
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident arm: inputs already in HBM --------------------------------
-    d_rhs = torch.from_numpy(rhs).cuda()
-    d_x = torch.zeros(N, dtype=torch.float64, device="cuda")
-    infos = []
+    def allmax(v):
+        if world == 1:
+            return float(v)
+        tt = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    # ---- the timed steps: fdal_solve with pinned HOST buffers; CUDA events inside bracket the device part
+    import ctypes as C
+
+    h_rhs = torch.from_numpy(rhs).pin_memory()
+    h_x = torch.zeros(N, dtype=torch.float64).pin_memory()
+    p_rhs = C.cast(h_rhs.data_ptr(), C.POINTER(C.c_double))
+    p_x = C.cast(h_x.data_ptr(), C.POINTER(C.c_double))
+
+    def one_step():
+        h_x.zero_()
+        info = b.SolveInfo()
+        st = ctx.api.solve(ctx._h, p_rhs, p_x, C.byref(info))
+        if st != 0:
+            raise RuntimeError(f"fdal_solve status {st}: {ctx.api.last_error(ctx._h)}")
+        return info
+
     for _ in range(args.warmup):
-        d_x.zero_()
-        torch.cuda.synchronize()
-        ctx.solve_dev(d_rhs.data_ptr(), d_x.data_ptr())
+        one_step()
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
-    t0 = time.perf_counter()
-    dev_ms = 0.0
+    t_region = time.perf_counter()
+    infos, walls = [], []
     for _ in range(args.steps):
-        d_x.zero_()
-        torch.cuda.synchronize()
-        info = ctx.solve_dev(d_rhs.data_ptr(), d_x.data_ptr())
-        dev_ms += info.solve_ms
-        infos.append(info)
-    barrier()
-    wall = time.perf_counter() - t0
-    clocks = sampler.stop()
-    ms_step = dev_ms / args.steps
-    if world > 1:
-        import torch.distributed as dist
-
-        tt = torch.tensor([ms_step], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms_step = float(tt.item())
-    x_dev = d_x.cpu().numpy()
-
-    # ---- end-to-end arm: host buffers through the reference-facing C-ABI call ---------
-    h_rhs = torch.from_numpy(rhs).pin_memory()
-    h_x = torch.zeros(N, dtype=torch.float64).pin_memory()
-    e2e_t = []
-    for i in range(min(args.warmup, 1) + args.steps):
-        h_x.zero_()
-        barrier()
         t0 = time.perf_counter()
-        info = b.SolveInfo()
-        import ctypes as C
-
-        st = ctx.api.solve(ctx._h, C.cast(h_rhs.data_ptr(), C.POINTER(C.c_double)),
-                           C.cast(h_x.data_ptr(), C.POINTER(C.c_double)), C.byref(info))
-        assert st == 0, st
+        infos.append(one_step())
         barrier()
-        if i >= min(args.warmup, 1):
-            e2e_t.append(time.perf_counter() - t0)
-    e2e_s = float(np.mean(e2e_t))
-    if world > 1:
-        import torch.distributed as dist
-
-        tt = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_s = float(tt.item())
+        walls.append(time.perf_counter() - t0)
+    barrier()
+    wall_total = time.perf_counter() - t_region
+    clocks = sampler.stop()
+    ms_step = allmax(float(np.mean([i.solve_ms for i in infos])))
+    e2e_s = allmax(float(np.mean(walls)))
+    x_loc = h_x.numpy().copy()
+    last = infos[-1]
+    log(f"rank {rank}: {args.steps} steps, {ms_step:.1f} ms/solve device, {e2e_s*1e3:.1f} ms end to end, "
+        f"{last.outer_iterations} outer / {last.inner_iterations} inner")
 
     # ---- per-kernel roofline, timed live with CUDA events on the library's stream ------
     peak, peak_src = measured_peak()
@@ -409,38 +442,73 @@ def run_ours(args, w, wname):
                               ("dot", b.TIME_DOT, 0), ("multidot16", b.TIME_MULTIDOT, 16), ("axpy", b.TIME_AXPY, 0)):
         try:
             ms, by, nl = ctx.time_kernel(what, param, warmup=3, reps=20, flush_l2=True)
+            ms = allmax(ms)
             kern[name] = {"ms": ms, "alg_bytes": by, "GBps": by / ms * 1e-6, "frac": by / ms * 1e-6 / peak,
                           "launches": nl}
         except Exception as e:  # e.g. multidot without FGMRES basis
             kern[name] = {"error": str(e)}
     dom = kern.get("cheb_fine", {})
     traffic = None
-    try:  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
+    try:  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of THIS workload
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
         if wname in tj and world == 1 and not args.nel and not args.no_bsr:
             traffic = tj[wname]["traffic_bytes_per_launch"]
     except Exception:
         pass
-    last = infos[-1]
-    total_dofs = n_dofs_global  # the whole (weak-scaled) job, all ranks together
+
+    # ---- parity object: correctness travels with every line (also in the scaling runs) ----
+    parity, cpu_sample = None, None
+    gathered = None
+    if world > 1:
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object((x_loc, rhs), gathered, dst=0, group=gloo)
+    if rank == 0 and not args.no_parity:
+        try:
+            if world == 1:
+                parity, cpu_sample = oracle_checks(prob, H, ctx, lp, x_loc, rhs, int(last.inner_iterations),
+                                                   max(1, os.cpu_count() or 1))
+            else:
+                xg = lp.gather([g[0] for g in gathered])
+                rg = lp.gather([g[1] for g in gathered])
+                parity = {"n_dofs": int(n_dofs_global)}
+                res = scipy_apply_system(prob, xg)
+                if res is not None:
+                    parity["true_residual_rel_scipy"] = float(np.linalg.norm(res - rg) / np.linalg.norm(rg))
+                parity["note"] = ("solution of the partitioned solve gathered on rank 0; AA x - b evaluated with scipy on the "
+                                  "global blocks (independent of the CUDA library and of the oracle)")
+        except Exception as e:
+            parity = {"error": f"{type(e).__name__}: {e}"}
+    if world > 1:
+        # the partitioned operator against scipy on a random vector (halo exchange, all-reduce of C x)
+        xr = np.random.default_rng(1).uniform(-1, 1, n_dofs_global)
+        y_loc = ctx.apply_system(lp.scatter(xr))
+        gy = [None] * world if rank == 0 else None
+        dist.gather_object(y_loc, gy, dst=0, group=gloo)
+        if rank == 0 and parity is not None and "error" not in parity:
+            ref = scipy_apply_system(prob, xr)
+            if ref is not None:
+                parity["apply_system_vs_scipy"] = float(np.linalg.norm(lp.gather(gy) - ref) / np.linalg.norm(ref))
+
     if rank == 0:
         res = {
-            "metric": METRIC, "value": total_dofs / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
+            "metric": METRIC, "value": n_dofs_global / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wname, "description": w["label"], "n_dofs": n_dofs_global, "blocks": lp.meta["sizes"],
-                       "parallelism": f"row-partitioned x{world}" if world > 1 else "single GPU",
-                       "nnz_A": lp.meta["nnz_A"], "amg_levels": lp.meta["amg_levels"],
-                       "l2_policy": "working set (matrices + hierarchy) larger than L2; kernel timings flush L2 "
-                                    "with a 256 MiB memset between launches",
-                       "outer_iterations": int(last.outer_iterations), "inner_iterations": int(last.inner_iterations),
-                       "mass_iterations": int(last.mass_iterations), "final_residual": last.final_residual,
-                       "setup_s": {"generate+amg_host": t_gen, "upload+finalize": t_setup},
-                       "wall_ms_per_step": wall / args.steps * 1e3, "graphs": bool(cfg.use_graphs),
-                       "block_size": int(cfg.block_size),
-                       "setup": "rank 0 builds and cuts the problem; shares via /dev/shm" if world > 1 else "in process"},
-            "e2e": {"value": total_dofs / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 16 * N, "d2h_bytes_per_step": 8 * N,
-                    "ms_per_step": e2e_s * 1e3},
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_of(wname, w, n_dofs_global, world, args.scaling),
+            "solve": {"outer_iterations": int(last.outer_iterations), "inner_iterations": int(last.inner_iterations),
+                      "mass_iterations": int(last.mass_iterations), "final_residual": last.final_residual,
+                      "ms_per_inner_iteration": ms_step / max(1, int(last.inner_iterations)),
+                      "blocks": lp.meta["sizes"], "nnz_A": lp.meta["nnz_A"], "amg_levels": lp.meta["amg_levels"],
+                      "parallelism": f"row-partitioned x{world}, {comm_mode}" if world > 1 else "single GPU",
+                      "l2_policy": "working set (matrices + hierarchy) larger than L2; kernel timings flush L2 "
+                                   "with a 256 MiB memset between launches",
+                      "setup_s": {"generate+amg_host": t_gen, "upload+finalize": t_setup},
+                      "timed_region_wall_s": wall_total, "graphs": bool(cfg.use_graphs),
+                      "block_size": int(cfg.block_size),
+                      "setup": "rank 0 builds and cuts the problem; shares via /dev/shm" if world > 1 else "in process"},
+            "e2e": {"value": n_dofs_global / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 16 * N, "d2h_bytes_per_step": 8 * N,
+                    "ms_per_step": e2e_s * 1e3,
+                    "how": "wall clock around fdal_solve (pinned host rhs + initial guess in, solution out), max over ranks"},
             "gpu_launches": int(sum(i.kernel_launches for i in infos)),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "fused Chebyshev step on the finest AMG level (k_bsr_spmv<B,TPR,EpiCheb> / k_spmv<TPR,EpiCheb>)",
@@ -449,19 +517,24 @@ def run_ours(args, w, wname):
                          "frac_of_nominal_8000GBs": (dom.get("GBps") / 8000.0) if dom.get("GBps") else None,
                          "peak_source": peak_src},
             "kernels": kern,
+            "parity": parity,
         }
-        if not args.no_cpu and world == 1:
-            n_outer = int(last.outer_iterations)
-            sprob, sH, note = bounded_cpu_problem(w, prob, H)
-            per_it, _ = cpu_sample(sprob, sH, threads=1, outer_steps=2)
-            res["cpu_baseline"] = {"value": sprob.n_dofs / (per_it * n_outer), "unit": UNIT, "cores": 1, "kind": "port",
-                                   "sample": f"first 2 outer FGMRES iterations of {note} (oracle, 1 thread = how the "
-                                             f"reference ships), extrapolated to {n_outer} outer iterations",
-                                   "ms_per_step_sample_problem": per_it * n_outer * 1e3, "n_dofs_sample": sprob.n_dofs}
+        if cpu_sample is not None:
+            n_inner = max(1, int(last.inner_iterations))
+            t1 = cpu_sample[1] * n_inner
+            tall = cpu_sample[max(cpu_sample)] * n_inner
+            res["cpu_baseline"] = {
+                "value": n_dofs_global / t1, "unit": UNIT, "cores": 1, "kind": "port",
+                "sample": f"one inner PCG iteration's dominant work (one AMG V-cycle + one augmented apply of the benched "
+                          f"{n_dofs_global}-DoF problem) by the oracle on 1 thread (how the reference ships): "
+                          f"{cpu_sample[1]:.2f} s, times the {n_inner} inner iterations of the solve; the complete CPU solve "
+                          f"is what `--impl reference` measures",
+                "all_cores": {"cores": max(cpu_sample), "value": n_dofs_global / tall, "s_per_inner_iteration": cpu_sample[max(cpu_sample)]},
+                "s_per_inner_iteration": cpu_sample[1]}
         emit(json.dumps(res))
+    ctx.close()
     if world > 1:
-        import torch.distributed as dist
-
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -471,18 +544,28 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("FDAL_BENCH_WORKLOAD", "stokes2d_1M"))
+    ap.add_argument("--workload", default=os.environ.get("FDAL_BENCH_WORKLOAD", DEFAULT_WORKLOAD))
     ap.add_argument("--nel", type=int, default=0, help="override the refinement of the workload")
-    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cycle", type=int, default=0, help="elliptic workload: refinement cycle")
+    ap.add_argument("--beta2", type=float, default=0.0, help="elliptic workload: coefficient of the inclusion")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong (default): the same problem on every GPU count; weak: the grid grows with the GPU count")
+    ap.add_argument("--no-cpu", "--no-parity", dest="no_parity", action="store_true",
+                    help="skip the oracle parity object and the CPU sample")
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--no-bsr", action="store_true")
-    ap.add_argument("--expected-outer", type=int, default=0)
     args = ap.parse_args()
     capture_stdout()
     w = dict(WORKLOADS[args.workload])
     if args.nel:
         w["nel"] = args.nel
         w["label"] = w["label"].rsplit("nel=", 1)[0] + f"nel={args.nel}"
+    if args.cycle and "cycle" in w:
+        w["cycle"] = args.cycle
+        w["label"] = w["label"].rsplit("cycle=", 1)[0] + f"cycle={args.cycle}"
+    if args.beta2 and w["kind"] == "elliptic":
+        w["beta2"] = args.beta2
+        w["label"] += f", beta2={args.beta2:g}"
     if args.impl == "reference":
         run_reference(args, w, args.workload)
     else:

@@ -138,6 +138,8 @@ DEVICE_SIGNATURES = {
         [c_void_p, c_int, c_int, c_int, c_int64, c_int64, _pi32, _pi32, _pi32],
     ),
     "amg_set_coarse_range": (c_int, [c_void_p, c_int, c_int64, c_int64]),
+    "amg_set_replicated_from": (c_int, [c_void_p, c_int, c_int]),
+    "comm_mode": (c_int, [c_void_p]),
 }
 # only the oracle has these
 ORACLE_SIGNATURES = {

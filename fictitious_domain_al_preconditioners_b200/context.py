@@ -216,8 +216,11 @@ class ALContext:
         Av, ka = b.csr_view(LH.coarse_A)
         nl = len(LH.levels)
         self._check(self.api.amg_set_coarse(self._h, which, nl, C.byref(Av)))
-        self._check(self.api.amg_set_coarse_range(self._h, which, int(LH.coarse_off[self.rank]),
-                                                  int(LH.coarse_off[self.rank + 1])))
+        if self.nranks > 1:
+            rep_from = LH.rep_from if LH.rep_from >= 0 else nl
+            self._check(self.api.amg_set_replicated_from(self._h, which, int(rep_from)))
+            self._check(self.api.amg_set_coarse_range(self._h, which, int(LH.coarse_off[self.rank]),
+                                                      int(LH.coarse_off[self.rank + 1])))
 
     def finalize(self):
         self._check(self.api.finalize(self._h))

@@ -36,6 +36,7 @@ struct NcclApi {
   decltype(&ncclCommInitRank) CommInitRank = nullptr;
   decltype(&ncclCommDestroy) CommDestroy = nullptr;
   decltype(&ncclAllReduce) AllReduce = nullptr;
+  decltype(&ncclAllGather) AllGather = nullptr;
   decltype(&ncclSend) Send = nullptr;
   decltype(&ncclRecv) Recv = nullptr;
   decltype(&ncclGroupStart) GroupStart = nullptr;
@@ -56,13 +57,14 @@ static NcclApi *nccl_api() {
   FDAL_SYM(CommInitRank);
   FDAL_SYM(CommDestroy);
   FDAL_SYM(AllReduce);
+  FDAL_SYM(AllGather);
   FDAL_SYM(Send);
   FDAL_SYM(Recv);
   FDAL_SYM(GroupStart);
   FDAL_SYM(GroupEnd);
   FDAL_SYM(GetErrorString);
 #undef FDAL_SYM
-  api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.Send && api.Recv &&
+  api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.AllGather && api.Send && api.Recv &&
            api.GroupStart && api.GroupEnd;
   return &api;
 }
@@ -100,15 +102,23 @@ static void host_transpose(const HostCsr &A, HostCsr &T) {
   T.set = true;
 }
 
+// one exchange channel (kernels.cuh: ChanDev) as the host sees it
+struct Chan {
+  ChanDev d;                   // device view, passed by value to the push / collect kernels
+  ChanDev *d_dev = nullptr;    // the same view in device memory (Reducer.ar, XVec.ch)
+  bool bcast = false;          // false: halo gather channel; true: all-gather / all-reduce channel
+  int cap = 0;                 // doubles per slot
+  std::vector<int> nb;         // neighbour ranks (bcast: all ranks, self included)
+  std::vector<int> nb_begin;   // gather: my send-list range per neighbour (nnb + 1)
+  std::vector<int64_t> src_off;  // [nranks] where rank q's entries start inside MY slot (-1: none)
+  size_t recv_off = 0, flags_off = 0, misc_off = 0;  // byte offsets inside the arena
+};
+
 struct DevCsr {
   CsrDev d;
   int *rp = nullptr, *ci = nullptr;
   double *v = nullptr;
   bool set = false;
-  // chunk plan of the TMA-staged kernel (k_spmv_stream)
-  int4 *desc = nullptr;
-  int nblk = 0;
-  bool stream_ok = false;
   // BSR copy (node-interleaved vector blocks): replaces the scalar arrays in the SpMV kernels
   BsrDev bsr;
   int bsr_b = 1;
@@ -118,9 +128,12 @@ struct DevCsr {
   bool dist_rows = false;  // rows are a partition: fused reductions need an all-reduce
   bool has_plan = false;
   int n_owned = std::numeric_limits<int>::max(), n_halo = 0, n_send = 0;
-  double *halo_buf = nullptr, *send_buf = nullptr;
+  double *halo_buf = nullptr, *send_buf = nullptr;  // NCCL fallback only
   int *send_idx = nullptr;
   std::vector<int> send_counts, recv_counts;
+  int chan = -1;            // index into fdal_ctx::chans (peer-channel mode)
+  int *order = nullptr;     // chunk order: interior chunks first (peer-channel mode)
+  int n_interior = 0;
 };
 
 struct AmgLevel {
@@ -135,10 +148,15 @@ struct AmgLevel {
 };
 struct Amg {
   std::vector<AmgLevel> lev;
-  double *cinv = nullptr;   // dense inverse of the (replicated) coarsest operator
-  double *cfull = nullptr;  // replicated coarse right-hand side (multi-GPU)
+  double *cinv = nullptr;   // dense inverse of the coarsest operator
   int cn_global = 0;        // rows of the coarsest operator
-  int64_t c_lo = 0, c_hi = -1;  // rows of it owned by this rank
+  // multi-GPU: levels [0, rep_from) are row-partitioned, levels >= rep_from are replicated on
+  // every rank (agglomeration: no halos, no collectives down there).  The restricted residual
+  // of level rep_from - 1 is all-gathered; rows [c_lo, c_hi) of level rep_from are this rank's.
+  int rep_from = -1;
+  int64_t c_lo = 0, c_hi = -1;
+  double *rown = nullptr;   // owned rows of the restricted residual before the all-gather
+  int gather_chan = -1;
   bool dist = false;
   bool ready = false;
 };
@@ -224,11 +242,20 @@ struct fdal_ctx {
   int64_t launches = 0, graph_launches = 0;
   // multi-GPU
   int rank = 0, nranks = 1;
-  ncclComm_t comm = nullptr;
+  ncclComm_t comm = nullptr;  // setup-time exchanges; per-iteration traffic only in the NCCL fallback mode
   int64_t n_dot_outer = 0;
-  int stream_ctas_per_sm = 3, spmv_unroll = 4, bsr_unroll = 1;
-  bool spmv_prefetch = false;  // FDAL_SPMV_PF=1: k_spmv / k_spmv2 with next-row-pointer and epilogue-operand prefetch
-  bool prefer_stream = false;
+  // peer channels (default with several ranks): every rank maps every other rank's arena with
+  // cudaIpc; halos, scalar / vector all-reduces and the coarse all-gather are direct NVLink
+  // stores + flags issued from this library's own kernels (FDAL_COMM=nccl: NCCL fallback)
+  bool p2p = false;
+  std::vector<Chan> chans;
+  char *arena = nullptr;
+  size_t arena_bytes = 0;
+  std::vector<char *> peer_arena;
+  int ch_scalar = -1, ch_vec = -1;
+  int vec_cap = 0;
+  int spmv_unroll = 4;
+  int bsr_unroll2 = 4, bsr_unroll3 = 1;  // blocks per lane in flight for 2x2 / 3x3 blocks (measured, profiles/)
   int fail = 0;
   std::vector<void *> allocs;
   std::string err;
@@ -315,7 +342,6 @@ static int build_bsr(fdal_ctx *c, const HostCsr &h, int b, DevCsr &d, bool *done
   std::vector<int> bcj((size_t)nblk);
   std::vector<double> bv((size_t)nblk * b * b, 0.0);
   // blocks stored contiguously (AoS): measured 25-40 % faster on B200 than per-row planes (profiles/)
-  const bool aos = getenv("FDAL_BSR_PLANES") == nullptr;
 #pragma omp parallel
   {
     std::vector<int> tmp;
@@ -334,10 +360,7 @@ static int build_bsr(fdal_ctx *c, const HostCsr &h, int b, DevCsr &d, bool *done
         for (int k = h.rp[I * b + r]; k < h.rp[I * b + r + 1]; ++k) {
           const int J = h.ci[k] / b, q = h.ci[k] % b;
           const int pos = (int)(std::lower_bound(tmp.begin(), tmp.end(), J) - tmp.begin());
-          if (aos)
-            vb[(size_t)pos * b * b + (r * b + q)] += h.v[k];
-          else
-            vb[(size_t)(r * b + q) * nb + pos] += h.v[k];
+          vb[(size_t)pos * b * b + (r * b + q)] += h.v[k];
         }
     }
   }
@@ -356,8 +379,9 @@ static int build_bsr(fdal_ctx *c, const HostCsr &h, int b, DevCsr &d, bool *done
   d.bsr.cj = dcj;
   d.bsr.v = dv;
   const double avg = (double)nblk / (double)nbr;
+  // measured on B200 (profiles/r2_kernel_probe.md): 2x2 blocks, 9-25 per row: 4 lanes x 4 blocks in
+  // flight; 3x3 blocks, ~64 per row: 16 lanes, one block each
   d.bsr.tpr = avg <= 6 ? 2 : avg <= 24 ? 4 : 16;
-  d.bsr.aos = aos ? 1 : 0;
   if (const char *e = getenv("FDAL_BSR_TPR")) {
     const int t = atoi(e);
     if (t == 2 || t == 4 || t == 8 || t == 16) d.bsr.tpr = t;
@@ -370,18 +394,45 @@ static int build_bsr(fdal_ctx *c, const HostCsr &h, int b, DevCsr &d, bool *done
   return FDAL_OK;
 }
 
+// chunk order of a row-partitioned matrix: chunks (the rows one CTA handles per loop trip)
+// whose rows only touch owned columns come first; the SpMV kernels acquire the halo before
+// the first chunk at a position >= n_interior, so the peers' pushes overlap the interior rows
+static int build_chunk_order(fdal_ctx *c, const HostCsr &h, DevCsr &d) {
+  const int unit = d.use_bsr ? d.bsr_b : 1;
+  const int tpr = d.use_bsr ? d.bsr.tpr : d.d.tpr;
+  const int64_t rpb = (int64_t)(kBlock / tpr) * unit;  // scalar rows per chunk
+  const int64_t nchunks = (h.nr + rpb - 1) / rpb;
+  std::vector<char> bnd((size_t)nchunks, 0);
+#pragma omp parallel for schedule(static)
+  for (int64_t q = 0; q < nchunks; ++q) {
+    const int64_t r0 = q * rpb, r1 = std::min<int64_t>(h.nr, r0 + rpb);
+    char f = 0;
+    for (int k = h.rp[r0]; k < h.rp[r1] && !f; ++k) f = h.ci[k] >= h.n_owned;
+    bnd[(size_t)q] = f;
+  }
+  std::vector<int> order;
+  order.reserve((size_t)nchunks);
+  for (int64_t q = 0; q < nchunks; ++q)
+    if (!bnd[(size_t)q]) order.push_back((int)q);
+  d.n_interior = (int)order.size();
+  for (int64_t q = 0; q < nchunks; ++q)
+    if (bnd[(size_t)q]) order.push_back((int)q);
+  int st;
+  if ((st = dmalloc(c, &d.order, (size_t)nchunks))) return st;
+  if (nchunks) CU(cudaMemcpyAsync(d.order, order.data(), (size_t)nchunks * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return FDAL_OK;
+}
+
 static int upload_csr(fdal_ctx *c, const HostCsr &h, DevCsr &d, int bsr_b = 1) {
   if (h.nnz >= (int64_t)std::numeric_limits<int>::max() || h.nr >= (int64_t)std::numeric_limits<int>::max()) {
     set_err(c, "matrix with %lld nnz exceeds the 32-bit row_ptr of this build", (long long)h.nnz);
     return FDAL_ERR_UNSUPPORTED;
   }
   int st;
-  // +8 zero-filled pad elements: the bulk copies of k_spmv_stream are 16-byte granular
   if ((st = dmalloc(c, &d.rp, (size_t)h.nr + 1))) return st;
-  if ((st = dmalloc(c, &d.ci, (size_t)h.nnz + 8))) return st;
-  if ((st = dmalloc(c, &d.v, (size_t)h.nnz + 8))) return st;
-  CU(cudaMemsetAsync(d.ci + h.nnz, 0, 8 * sizeof(int), c->stream));
-  CU(cudaMemsetAsync(d.v + h.nnz, 0, 8 * sizeof(double), c->stream));
+  if ((st = dmalloc(c, &d.ci, (size_t)h.nnz))) return st;
+  if ((st = dmalloc(c, &d.v, (size_t)h.nnz))) return st;
   CU(cudaMemcpyAsync(d.rp, h.rp.data(), ((size_t)h.nr + 1) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
   if (h.nnz) {
     CU(cudaMemcpyAsync(d.ci, h.ci.data(), (size_t)h.nnz * sizeof(int), cudaMemcpyHostToDevice, c->stream));
@@ -407,34 +458,35 @@ static int upload_csr(fdal_ctx *c, const HostCsr &h, DevCsr &d, int bsr_b = 1) {
     d.n_send = (int)h.send_idx.size();
     d.send_counts = h.send_counts;
     d.recv_counts = h.recv_counts;
-    if ((st = dvec(c, &d.halo_buf, d.n_halo))) return st;
-    if ((st = dvec(c, &d.send_buf, d.n_send))) return st;
     if ((st = dmalloc(c, &d.send_idx, (size_t)d.n_send))) return st;
     if (d.n_send)
       CU(cudaMemcpyAsync(d.send_idx, h.send_idx.data(), (size_t)d.n_send * sizeof(int), cudaMemcpyHostToDevice,
                          c->stream));
     CU(cudaStreamSynchronize(c->stream));
-  }
-  // chunk plan: runs of whole rows whose 4-aligned non-zero range fits kChunk
-  {
-    const bool no_stream = getenv("FDAL_NO_STREAM") != nullptr;
-    std::vector<int4> rb;
-    bool ok = !no_stream && h.nr > 0;
-    int64_t r0 = 0;
-    while (ok && r0 < h.nr) {
-      const int e0 = h.rp[r0] & ~3;
-      int64_t r1 = r0;
-      while (r1 < h.nr && r1 - r0 < 4096 && ((h.rp[r1 + 1] + 3) & ~3) - e0 <= kChunk) ++r1;
-      if (r1 == r0) ok = false;  // a single row longer than a chunk: keep the row-group kernel
-      rb.push_back(make_int4((int)r0, (int)r1, e0, ((h.rp[r1] + 3) & ~3) - e0));
-      r0 = r1;
-    }
-    if (ok) {
-      d.nblk = (int)rb.size();
-      if ((st = dmalloc(c, &d.desc, rb.size()))) return st;
-      CU(cudaMemcpyAsync(d.desc, rb.data(), rb.size() * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
-      CU(cudaStreamSynchronize(c->stream));
-      d.stream_ok = true;
+    if (c->p2p) {
+      // register a gather channel: neighbours = ranks I send to or receive from (a symmetric relation)
+      Chan ch;
+      ch.bcast = false;
+      ch.cap = d.n_halo;
+      ch.src_off.assign((size_t)c->nranks, -1);
+      ch.nb_begin.push_back(0);
+      int64_t ro = 0;
+      int so = 0;
+      for (int q = 0; q < c->nranks; ++q) {
+        if (h.recv_counts[q]) ch.src_off[(size_t)q] = ro;
+        ro += h.recv_counts[q];
+        if (h.send_counts[q] || h.recv_counts[q]) {
+          ch.nb.push_back(q);
+          so += h.send_counts[q];
+          ch.nb_begin.push_back(so);
+        }
+      }
+      d.chan = (int)c->chans.size();
+      c->chans.push_back(ch);
+      if ((st = build_chunk_order(c, h, d))) return st;
+    } else {
+      if ((st = dvec(c, &d.halo_buf, d.n_halo))) return st;
+      if ((st = dvec(c, &d.send_buf, d.n_send))) return st;
     }
   }
   return FDAL_OK;
@@ -450,17 +502,71 @@ static inline int grid_elems(const fdal_ctx *c, long long n) {
   long long g = (n + kBlock - 1) / kBlock;
   return (int)std::max<long long>(1, std::min<long long>(g, (long long)c->sms * kMaxGridPerSM));
 }
-static inline Reducer reducer(fdal_ctx *c, double *out) { return Reducer{c->d_partials, c->d_counter, out}; }
+// dist: the value is a partial over this rank's rows -> the finishing block of the kernel
+// all-reduces it over the ranks through the scalar channel (peer-channel mode)
+static inline Reducer reducer(fdal_ctx *c, double *out, bool dist = false) {
+  Reducer R{c->d_partials, c->d_counter, out, nullptr};
+  if (dist && c->p2p) R.ar = c->chans[(size_t)c->ch_scalar].d_dev;
+  return R;
+}
 
-// sum of device doubles over all ranks, in stream order (NVLink / NVSwitch through NCCL)
-static void allreduce(fdal_ctx *c, double *p, size_t count) {
+static void launch_check(fdal_ctx *c) {
+  const cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess && !c->fail) {
+    set_err(c, "kernel launch failed: %s", cudaGetErrorString(e));
+    c->fail = FDAL_ERR_CUDA;
+  }
+}
+// NCCL fallback: sum of device doubles over all ranks, in stream order
+static void nccl_allreduce(fdal_ctx *c, double *p, size_t count) {
   if (c->nranks <= 1 || !count) return;
   ncclResult_t r = nccl_api()->AllReduce(p, p, count, ncclDouble, ncclSum, c->comm, c->stream);
   if (r != ncclSuccess && !c->fail) c->fail = FDAL_ERR_NCCL;
 }
-// fill A's halo buffer with the owners' entries of x: pack -> grouped send/recv
+// after a kernel with a fused reduction over partitioned rows: in peer-channel mode the kernel
+// has already all-reduced the scalar itself
+static void finish_scalar(fdal_ctx *c, double *p, size_t count, bool dist) {
+  if (dist && c->nranks > 1 && !c->p2p) nccl_allreduce(c, p, count);
+}
+static int chan_grid(fdal_ctx *c, int n) { return std::max(1, std::min((n + kBlock - 1) / kBlock, c->sms)); }
+// in-place sum of a replicated-size vector (C x partials, count <= vec_cap) over all ranks
+static void allreduce_vec(fdal_ctx *c, double *p, size_t count) {
+  if (c->nranks <= 1 || !count) return;
+  if (!c->p2p) {
+    nccl_allreduce(c, p, count);
+    return;
+  }
+  const Chan &ch = c->chans[(size_t)c->ch_vec];
+  k_chan_push_bcast<<<dim3(chan_grid(c, (int)count), c->nranks), kBlock, 0, c->stream>>>(ch.d, p, (int)count);
+  k_chan_collect<true><<<chan_grid(c, (int)count), kBlock, 0, c->stream>>>(ch.d, p, (int)count, c->vec_cap);
+  c->launches += 2;
+}
+// all-gather of the owned rows of a vector into the replicated vector `full` (n_full entries)
+static void allgather_rows(fdal_ctx *c, Amg &g, const double *own, int n_own, double *full, int n_full) {
+  if (!c->p2p) {
+    cudaMemsetAsync(full, 0, (size_t)n_full * sizeof(double), c->stream);
+    if (n_own)
+      cudaMemcpyAsync(full + g.c_lo, own, (size_t)n_own * sizeof(double), cudaMemcpyDeviceToDevice, c->stream);
+    nccl_allreduce(c, full, (size_t)n_full);
+    return;
+  }
+  const Chan &ch = c->chans[(size_t)g.gather_chan];
+  k_chan_push_bcast<<<dim3(chan_grid(c, n_own), c->nranks), kBlock, 0, c->stream>>>(ch.d, own, n_own);
+  k_chan_collect<false><<<chan_grid(c, n_full), kBlock, 0, c->stream>>>(ch.d, full, n_full, 0);
+  c->launches += 2;
+}
+// make the owners' entries of x visible in A's halo: peer-channel mode pushes my entries straight
+// into the neighbours' receive slots (one kernel; the SpMV that follows acquires the flags before its
+// first boundary chunk); NCCL fallback: pack -> grouped send/recv
 static void halo_exchange(fdal_ctx *c, const DevCsr &A, const double *x) {
   if (!A.has_plan || c->nranks <= 1) return;
+  if (c->p2p) {
+    const Chan &ch = c->chans[(size_t)A.chan];
+    if (ch.nb.empty()) return;
+    k_chan_push_gather<<<chan_grid(c, A.n_send), kBlock, 0, c->stream>>>(ch.d, A.send_idx, x);
+    c->launches++;
+    return;
+  }
   if (A.n_send) {
     k_pack<<<grid_elems(c, A.n_send), kBlock, 0, c->stream>>>(A.n_send, A.send_idx, x, A.send_buf);
     c->launches++;
@@ -477,54 +583,31 @@ static void halo_exchange(fdal_ctx *c, const DevCsr &A, const double *x) {
   ncclResult_t r = n->GroupEnd();
   if (r != ncclSuccess && !c->fail) c->fail = FDAL_ERR_NCCL;
 }
-static inline XVec xv(const DevCsr &A, const double *x) { return XVec{x, A.halo_buf, A.n_owned}; }
-
-template <class Epi, bool TWO>
-static void spmv_stream(fdal_ctx *c, const DevCsr &A, const double *x, const DevCsr *B2, const double *t2, Epi epi,
-                        double *red_out) {
-  const int g = std::max(1, std::min(A.nblk, c->sms * c->stream_ctas_per_sm));
-  Reducer R = reducer(c, red_out);
-  XVec X = xv(A, x);
-  StreamPlan plan{A.desc, A.nblk};
-  CsrDev b2 = B2 ? B2->d : CsrDev();
-  const size_t sm = kStreamSmemBytes;
-  static bool attr_done = false;  // per (Epi, TWO) instantiation
-  if (!attr_done) {
-    cudaFuncSetAttribute(k_spmv_stream<2, Epi, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    cudaFuncSetAttribute(k_spmv_stream<4, Epi, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    cudaFuncSetAttribute(k_spmv_stream<8, Epi, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    cudaFuncSetAttribute(k_spmv_stream<16, Epi, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    cudaFuncSetAttribute(k_spmv_stream<32, Epi, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    attr_done = true;
+static inline XVec xv(const fdal_ctx *c, const DevCsr &A, const double *x) {
+  XVec X{x, A.halo_buf, A.n_owned};
+  if (c->p2p && A.chan >= 0 && !c->chans[(size_t)A.chan].nb.empty()) {
+    X.ch = c->chans[(size_t)A.chan].d_dev;
+    X.order = A.order;
+    X.n_interior = A.n_interior;
   }
-  switch (A.d.tpr) {
-    case 2: k_spmv_stream<2, Epi, TWO><<<g, kBlock, sm, c->stream>>>(A.d, plan, X, b2, t2, epi, R); break;
-    case 4: k_spmv_stream<4, Epi, TWO><<<g, kBlock, sm, c->stream>>>(A.d, plan, X, b2, t2, epi, R); break;
-    case 8: k_spmv_stream<8, Epi, TWO><<<g, kBlock, sm, c->stream>>>(A.d, plan, X, b2, t2, epi, R); break;
-    case 16: k_spmv_stream<16, Epi, TWO><<<g, kBlock, sm, c->stream>>>(A.d, plan, X, b2, t2, epi, R); break;
-    default: k_spmv_stream<32, Epi, TWO><<<g, kBlock, sm, c->stream>>>(A.d, plan, X, b2, t2, epi, R); break;
-  }
-  c->launches++;
-  if (red_out && A.dist_rows) allreduce(c, red_out, 1);
+  return X;
 }
+
 template <class Epi, bool TWO>
 static void spmv_bsr(fdal_ctx *c, const DevCsr &A, const double *x, const DevCsr *B2, const double *t2, Epi epi,
                      double *red_out) {
   const int tpr = A.bsr.tpr;
   const int g = grid_rows(c, A.bsr.nbrows, tpr);
-  Reducer R = reducer(c, red_out);
-  XVec X = xv(A, x);
+  Reducer R = reducer(c, red_out, A.dist_rows);
+  XVec X = xv(c, A, x);
   CsrDev b2 = B2 ? B2->d : CsrDev();
-#define FDAL_BSR_LAUNCH(BB, TT)                                                                     \
-  do {                                                                                              \
-    if (!A.bsr.aos)                                                                                 \
-      k_bsr_spmv<BB, TT, Epi, TWO, false><<<g, kBlock, 0, c->stream>>>(A.bsr, X, b2, t2, epi, R);   \
-    else if (c->bsr_unroll >= 4)                                                                    \
-      k_bsr_spmv<BB, TT, Epi, TWO, true, 4><<<g, kBlock, 0, c->stream>>>(A.bsr, X, b2, t2, epi, R); \
-    else if (c->bsr_unroll > 1)                                                                     \
-      k_bsr_spmv<BB, TT, Epi, TWO, true, 2><<<g, kBlock, 0, c->stream>>>(A.bsr, X, b2, t2, epi, R); \
-    else                                                                                            \
-      k_bsr_spmv<BB, TT, Epi, TWO, true><<<g, kBlock, 0, c->stream>>>(A.bsr, X, b2, t2, epi, R);    \
+  const int unroll = A.bsr_b == 2 ? c->bsr_unroll2 : c->bsr_unroll3;
+#define FDAL_BSR_LAUNCH(BB, TT)                                                               \
+  do {                                                                                        \
+    if (unroll >= 4)                                                                          \
+      k_bsr_spmv<BB, TT, Epi, TWO, 4><<<g, kBlock, 0, c->stream>>>(A.bsr, X, b2, t2, epi, R); \
+    else                                                                                      \
+      k_bsr_spmv<BB, TT, Epi, TWO, 1><<<g, kBlock, 0, c->stream>>>(A.bsr, X, b2, t2, epi, R); \
   } while (0)
   if (A.bsr_b == 2) {
     switch (tpr) {
@@ -535,7 +618,6 @@ static void spmv_bsr(fdal_ctx *c, const DevCsr &A, const double *x, const DevCsr
     }
   } else {
     switch (tpr) {
-      case 2: FDAL_BSR_LAUNCH(3, 2); break;
       case 4: FDAL_BSR_LAUNCH(3, 4); break;
       case 16: FDAL_BSR_LAUNCH(3, 16); break;
       default: FDAL_BSR_LAUNCH(3, 8); break;
@@ -543,15 +625,21 @@ static void spmv_bsr(fdal_ctx *c, const DevCsr &A, const double *x, const DevCsr
   }
 #undef FDAL_BSR_LAUNCH
   c->launches++;
-  if (red_out && A.dist_rows) allreduce(c, red_out, 1);
+  launch_check(c);
+  finish_scalar(c, red_out, red_out ? 1 : 0, A.dist_rows);
 }
 template <class Epi>
 static void spmv(fdal_ctx *c, const DevCsr &A, const double *x, Epi epi, double *red_out = nullptr) {
   halo_exchange(c, A, x);
   if (A.d.nrows == 0) {
     if (red_out) {
-      cudaMemsetAsync(red_out, 0, sizeof(double), c->stream);
-      if (A.dist_rows) allreduce(c, red_out, 1);
+      if (A.dist_rows && c->p2p) {  // still take part in the fused all-reduce
+        k_dot<<<1, kBlock, 0, c->stream>>>(0, x, x, reducer(c, red_out, true));
+        c->launches++;
+      } else {
+        cudaMemsetAsync(red_out, 0, sizeof(double), c->stream);
+        finish_scalar(c, red_out, 1, A.dist_rows);
+      }
     }
     return;
   }
@@ -559,22 +647,10 @@ static void spmv(fdal_ctx *c, const DevCsr &A, const double *x, Epi epi, double 
     spmv_bsr<Epi, false>(c, A, x, nullptr, nullptr, epi, red_out);
     return;
   }
-  if (A.stream_ok && c->prefer_stream) {
-    spmv_stream<Epi, false>(c, A, x, nullptr, nullptr, epi, red_out);
-    return;
-  }
   const int g = grid_rows(c, A.d.nrows, A.d.tpr);
-  Reducer R = reducer(c, red_out);
-  XVec X = xv(A, x);
-  if (c->spmv_prefetch) {
-    switch (A.d.tpr) {
-      case 2: k_spmv<2, Epi, 4, true><<<g, kBlock, 0, c->stream>>>(A.d, X, epi, R); break;
-      case 4: k_spmv<4, Epi, 4, true><<<g, kBlock, 0, c->stream>>>(A.d, X, epi, R); break;
-      case 8: k_spmv<8, Epi, 4, true><<<g, kBlock, 0, c->stream>>>(A.d, X, epi, R); break;
-      case 16: k_spmv<16, Epi, 4, true><<<g, kBlock, 0, c->stream>>>(A.d, X, epi, R); break;
-      default: k_spmv<32, Epi, 4, true><<<g, kBlock, 0, c->stream>>>(A.d, X, epi, R); break;
-    }
-  } else if (c->spmv_unroll > 1) {
+  Reducer R = reducer(c, red_out, A.dist_rows);
+  XVec X = xv(c, A, x);
+  if (c->spmv_unroll > 1) {
     switch (A.d.tpr) {
       case 2: k_spmv<2, Epi, 4><<<g, kBlock, 0, c->stream>>>(A.d, X, epi, R); break;
       case 4: k_spmv<4, Epi, 4><<<g, kBlock, 0, c->stream>>>(A.d, X, epi, R); break;
@@ -592,7 +668,8 @@ static void spmv(fdal_ctx *c, const DevCsr &A, const double *x, Epi epi, double 
     }
   }
   c->launches++;
-  if (red_out && A.dist_rows) allreduce(c, red_out, 1);
+  launch_check(c);
+  finish_scalar(c, red_out, red_out ? 1 : 0, A.dist_rows);
 }
 template <class Epi>
 static void spmv2(fdal_ctx *c, const DevCsr &A, const double *x, const DevCsr &Ct, const double *t, Epi epi,
@@ -600,8 +677,13 @@ static void spmv2(fdal_ctx *c, const DevCsr &A, const double *x, const DevCsr &C
   halo_exchange(c, A, x);
   if (A.d.nrows == 0) {
     if (red_out) {
-      cudaMemsetAsync(red_out, 0, sizeof(double), c->stream);
-      if (A.dist_rows) allreduce(c, red_out, 1);
+      if (A.dist_rows && c->p2p) {
+        k_dot<<<1, kBlock, 0, c->stream>>>(0, x, x, reducer(c, red_out, true));
+        c->launches++;
+      } else {
+        cudaMemsetAsync(red_out, 0, sizeof(double), c->stream);
+        finish_scalar(c, red_out, 1, A.dist_rows);
+      }
     }
     return;
   }
@@ -609,22 +691,10 @@ static void spmv2(fdal_ctx *c, const DevCsr &A, const double *x, const DevCsr &C
     spmv_bsr<Epi, true>(c, A, x, &Ct, t, epi, red_out);
     return;
   }
-  if (A.stream_ok && c->prefer_stream) {
-    spmv_stream<Epi, true>(c, A, x, &Ct, t, epi, red_out);
-    return;
-  }
   const int g = grid_rows(c, A.d.nrows, A.d.tpr);
-  Reducer R = reducer(c, red_out);
-  XVec X = xv(A, x);
-  if (c->spmv_prefetch) {
-    switch (A.d.tpr) {
-      case 2: k_spmv2<2, Epi, 4, true><<<g, kBlock, 0, c->stream>>>(A.d, X, Ct.d, t, epi, R); break;
-      case 4: k_spmv2<4, Epi, 4, true><<<g, kBlock, 0, c->stream>>>(A.d, X, Ct.d, t, epi, R); break;
-      case 8: k_spmv2<8, Epi, 4, true><<<g, kBlock, 0, c->stream>>>(A.d, X, Ct.d, t, epi, R); break;
-      case 16: k_spmv2<16, Epi, 4, true><<<g, kBlock, 0, c->stream>>>(A.d, X, Ct.d, t, epi, R); break;
-      default: k_spmv2<32, Epi, 4, true><<<g, kBlock, 0, c->stream>>>(A.d, X, Ct.d, t, epi, R); break;
-    }
-  } else if (c->spmv_unroll > 1) {
+  Reducer R = reducer(c, red_out, A.dist_rows);
+  XVec X = xv(c, A, x);
+  if (c->spmv_unroll > 1) {
     switch (A.d.tpr) {
       case 2: k_spmv2<2, Epi, 4><<<g, kBlock, 0, c->stream>>>(A.d, X, Ct.d, t, epi, R); break;
       case 4: k_spmv2<4, Epi, 4><<<g, kBlock, 0, c->stream>>>(A.d, X, Ct.d, t, epi, R); break;
@@ -642,13 +712,14 @@ static void spmv2(fdal_ctx *c, const DevCsr &A, const double *x, const DevCsr &C
     }
   }
   c->launches++;
-  if (red_out && A.dist_rows) allreduce(c, red_out, 1);
+  launch_check(c);
+  finish_scalar(c, red_out, red_out ? 1 : 0, A.dist_rows);
 }
 // out = a[0:n) . b[0:n); dist: n is this rank's share, all-reduced over the ranks
 static void dot(fdal_ctx *c, int64_t n, const double *a, const double *b, double *out, bool dist = false) {
-  k_dot<<<grid_elems(c, std::max<int64_t>(n, 1)), kBlock, 0, c->stream>>>(n, a, b, reducer(c, out));
+  k_dot<<<grid_elems(c, std::max<int64_t>(n, 1)), kBlock, 0, c->stream>>>(n, a, b, reducer(c, out, dist));
   c->launches++;
-  if (dist) allreduce(c, out, 1);
+  finish_scalar(c, out, 1, dist);
 }
 static void axpby(fdal_ctx *c, int64_t n, double a, const double *x, double b, double *y) {
   if (n == 0) return;
@@ -675,6 +746,8 @@ static void dzero(fdal_ctx *c, int64_t n, double *y) {
 static int read_scalars(fdal_ctx *c, const double *d, int count, double *out) {
   CU(cudaMemcpyAsync(c->h_scal, d, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());  // a failed launch must not pass for a converged scalar
+  if (c->fail == FDAL_ERR_CUDA) return c->fail;
   memcpy(out, c->h_scal, (size_t)count * sizeof(double));
   return FDAL_OK;
 }
@@ -727,20 +800,12 @@ static double *cheb(fdal_ctx *c, AmgLevel &L, const double *b, double *xcur, boo
   }
   return cur;
 }
-// coarsest level: x = A_L^-1 b.  Multi-GPU: the right-hand side is all-reduced into a
-// replicated vector and every rank applies its rows of the replicated inverse.
-static void coarse_solve(fdal_ctx *c, Amg &g, const double *b_local, double *x_local) {
+// coarsest level: x = A_L^-1 b (dense inverse, L2-resident).  With several ranks the coarsest
+// level is always inside the replicated part of the hierarchy: every rank applies the whole inverse.
+static void coarse_solve(fdal_ctx *c, Amg &g, const double *b, double *x) {
   AmgLevel &C = g.lev.back();
-  const double *rhs = b_local;
-  if (g.dist) {
-    dzero(c, g.cn_global, g.cfull);
-    dcopy(c, C.n, b_local, g.cfull + g.c_lo);
-    allreduce(c, g.cfull, (size_t)g.cn_global);
-    rhs = g.cfull;
-  }
   if (C.n > 0) {
-    k_gemv<<<(C.n * 32 + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(C.n, g.cn_global,
-                                                                       g.cinv + (size_t)g.c_lo * g.cn_global, rhs, x_local);
+    k_gemv<<<(C.n * 32 + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(C.n, g.cn_global, g.cinv, b, x);
     c->launches++;
   }
 }
@@ -749,7 +814,7 @@ static void vcycle(fdal_ctx *c, Amg &g, const double *b0, double *z, double *red
   const int nl = (int)g.lev.size();
   if (nl == 1) {
     coarse_solve(c, g, b0, z);
-    if (red_out) dot(c, g.lev[0].n, b0, z, red_out, g.dist);
+    if (red_out) dot(c, g.lev[0].n, b0, z, red_out, false);
     return;
   }
   std::vector<double *> xres(nl, nullptr);
@@ -758,7 +823,14 @@ static void vcycle(fdal_ctx *c, Amg &g, const double *b0, double *z, double *red
     const double *bl = l == 0 ? b0 : L.b;
     double *x = cheb(c, L, bl, L.xa, true, nullptr, nullptr);
     spmv(c, L.A, x, EpiResid{L.r, bl});
-    spmv(c, L.R, L.r, EpiAssign{g.lev[l + 1].b, 1.0});
+    if (g.dist && l + 1 == g.rep_from) {
+      // last partitioned level: restrict onto the owned coarse rows, then all-gather the
+      // replicated right-hand side of the agglomerated levels
+      spmv(c, L.R, L.r, EpiAssign{g.rown, 1.0});
+      allgather_rows(c, g, g.rown, (int)(g.c_hi - g.c_lo), g.lev[l + 1].b, g.lev[l + 1].n);
+    } else {
+      spmv(c, L.R, L.r, EpiAssign{g.lev[l + 1].b, 1.0});
+    }
     xres[l] = x;
   }
   {
@@ -792,9 +864,9 @@ static void cg_body(fdal_ctx *c, CgWs &w, const OpFn &op, const OpFn &prec, doub
   c->launches++;
   op(w.p, w.v, w.scal + S_PV);
   k_cg_update_xr<<<grid_elems(c, n), kBlock, 0, c->stream>>>(n, w.dist ? w.n_dot : n, w.p, w.v, x, w.r, w.scal,
-                                                               reducer(c, w.scal + S_RR));
+                                                               reducer(c, w.scal + S_RR, w.dist));
   c->launches++;
-  if (w.dist) allreduce(c, w.scal + S_RR, 1);
+  finish_scalar(c, w.scal + S_RR, 1, w.dist);
 }
 static bool stream_is_capturing(fdal_ctx *c) {
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
@@ -837,7 +909,7 @@ static void run_cg_body(fdal_ctx *c, CgWs &w, const OpFn &op, const OpFn &prec, 
     if (!w.body_exec)
       w.graph_ok = capture_graph(c, [&]() { cg_body(c, w, op, prec, w.x); }, &w.body_exec, &w.body_nodes);
     if (w.body_exec) {
-      cudaGraphLaunch(w.body_exec, c->stream);
+      if (cudaGraphLaunch(w.body_exec, c->stream) != cudaSuccess && !c->fail) c->fail = FDAL_ERR_CUDA;
       c->launches += w.body_nodes;
       c->graph_launches++;
       return;
@@ -875,9 +947,9 @@ static int cg_solve(fdal_ctx *c, CgWs &w, const OpFn &op, const OpFn &prec, cons
 static void mass_prec(fdal_ctx *c, const double *invdiag, int64_t n, const double *r, double *z, double *dot_out,
                       bool dist = false) {
   k_diag_prec_dot<<<grid_elems(c, std::max<int64_t>(n, 1)), kBlock, 0, c->stream>>>(n, invdiag, r, z,
-                                                                                   reducer(c, dot_out));
+                                                                                   reducer(c, dot_out, dist));
   c->launches++;
-  if (dist) allreduce(c, dot_out, 1);
+  finish_scalar(c, dot_out, 1, dist);
 }
 static void mass_solve_fixed(fdal_ctx *c, CgWs &w, const DevCsr &M, const double *invdiag, int its, const double *b,
                              double *x) {
@@ -892,7 +964,7 @@ static void mass_solve_fixed(fdal_ctx *c, CgWs &w, const DevCsr &M, const double
   if (graphs_enabled(c) && w.graph_ok && !stream_is_capturing(c)) {
     if (!w.fixed_exec) w.graph_ok = capture_graph(c, whole, &w.fixed_exec, &w.fixed_nodes);
     if (w.fixed_exec) {
-      cudaGraphLaunch(w.fixed_exec, c->stream);
+      if (cudaGraphLaunch(w.fixed_exec, c->stream) != cudaSuccess && !c->fail) c->fail = FDAL_ERR_CUDA;
       c->launches += w.fixed_nodes;
       c->graph_launches++;
       done = true;
@@ -929,6 +1001,9 @@ static int mass_calibrate(fdal_ctx *c, CgWs &w, const DevCsr &M, const double *i
     if ((st = read_scalars(c, w.scal + S_RR, 1, &rr))) return st;
   }
   *its_out = std::min(cap, it + 3);
+  if (it >= cap && std::sqrt(std::fabs(rr)) > 1e-17 * std::sqrt(rr0))
+    set_err(c, "warning: the exact mass solve stopped at its cap of %d Jacobi-PCG iterations with relative residual %.2e",
+            cap, std::sqrt(std::fabs(rr) / rr0));
   return FDAL_OK;
 }
 
@@ -958,13 +1033,7 @@ static void apply_winv_scaled(fdal_ctx *c, double a, const double *x, double *y,
     // whole fixed-count PCG (both applications of M^-1 for W = M^2) in one CTA
     const int threads = (int)std::min<int64_t>(kMassCtaThreads, ((m + 31) / 32) * 32);
     if (m <= kMassCtaSmemRows) {
-      const size_t sm = (size_t)4 * m * sizeof(double);
-      static bool attr_done = false;
-      if (!attr_done) {
-        cudaFuncSetAttribute(k_mass_pcg_cta<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)(4 * kMassCtaSmemRows * sizeof(double)));
-        attr_done = true;
-      }
+      const size_t sm = (size_t)4 * m * sizeof(double);  // opt-in above 48 KB: set in fdal_finalize, per device
       k_mass_pcg_cta<true><<<1, threads, sm, c->stream>>>(c->dmat[FDAL_MAT_M].d, c->d_m_invdiag, c->mass_its_m, repeat,
                                                           a, x, add, y, c->mass_cta_ws);
     } else {
@@ -1007,7 +1076,7 @@ static void couple_phase1(fdal_ctx *c, const double *x, double a, const double *
     // C holds this rank's columns: partial sums, all-reduced over the m multiplier rows
     double *w = (y1 && c->cfg.winv_mode != FDAL_WINV_DIAG) ? y1 : c->t_m1;
     spmv(c, C, x, EpiAssign{w, 1.0});
-    allreduce(c, w, (size_t)c->m);
+    allreduce_vec(c, w, (size_t)c->m);
     if (c->cfg.winv_mode == FDAL_WINV_DIAG) {
       k_couple_elem<<<grid_elems(c, c->m), kBlock, 0, c->stream>>>((int)c->m, w, c->d_winv, a, add, y1, t);
       c->launches++;
@@ -1093,7 +1162,7 @@ static void apply_aug(fdal_ctx *c, int which, const double *x, double *y, double
 // (the four LinearOperator blocks of elliptic_interface.cc:807-813 share tw)
 static void elliptic_w(fdal_ctx *c, const double *x0, const double *x1, double *w) {
   spmv(c, c->dmat[FDAL_MAT_C], x0, EpiAssign{w, 1.0});
-  allreduce(c, w, (size_t)c->m);
+  allreduce_vec(c, w, (size_t)c->m);
   spmv(c, c->dmat[FDAL_MAT_M], x1, EpiAdd{w, -1.0});
 }
 static void apply_aug_block(fdal_ctx *c, const double *x, double *y, double *dot_out) {
@@ -1118,7 +1187,7 @@ static void apply_system(fdal_ctx *c, const double *x, double *y) {
       // y0 = A x0 + Ct (gamma invW C x0 + x1) ; y1 = C x0
       if (c->cfg.aug_explicit) {
         spmv(c, c->dmat[FDAL_MAT_C], x0, EpiAssign{y1, 1.0});
-        allreduce(c, y1, (size_t)c->m);
+        allreduce_vec(c, y1, (size_t)c->m);
         spmv2(c, A, x0, Ct, x1, EpiAssign{y0, 1.0});
       } else {
         couple_phase1(c, x0, c->cfg.gamma, x1, y1, c->t_m0);
@@ -1129,7 +1198,7 @@ static void apply_system(fdal_ctx *c, const double *x, double *y) {
     case FDAL_KIND_STOKES_DIAG_MINRES:
       if (c->cfg.aug_explicit) {
         spmv(c, c->dmat[FDAL_MAT_C], x0, EpiAssign{y2, 1.0});
-        allreduce(c, y2, (size_t)c->m);
+        allreduce_vec(c, y2, (size_t)c->m);
         spmv2(c, A, x0, Ct, x2, EpiAssign{y0, 1.0});
       } else {
         couple_phase1(c, x0, c->cfg.gamma, x2, y2, c->t_m0);
@@ -1299,11 +1368,11 @@ static int fgmres(fdal_ctx *c, const double *b, double *x, fdal_solve_info *info
       const int nv = j + 1;
       double *h1 = c->d_h, *h2 = c->d_h + (mb + 2);
       const int gd = grid_elems(c, N);
-      k_multidot<<<gd, kBlock, 0, c->stream>>>(N, Nd, w, c->V, N, nv, 0, reducer(c, h1));
-      if (dist) allreduce(c, h1, (size_t)nv);
+      k_multidot<<<gd, kBlock, 0, c->stream>>>(N, Nd, w, c->V, N, nv, 0, reducer(c, h1, dist));
+      finish_scalar(c, h1, (size_t)nv, dist);
       k_multiaxpy<<<gd, kBlock, 0, c->stream>>>(N, w, c->V, N, nv, h1, -1.0);
-      k_multidot<<<gd, kBlock, 0, c->stream>>>(N, Nd, w, c->V, N, nv, 0, reducer(c, h2));
-      if (dist) allreduce(c, h2, (size_t)nv);
+      k_multidot<<<gd, kBlock, 0, c->stream>>>(N, Nd, w, c->V, N, nv, 0, reducer(c, h2, dist));
+      finish_scalar(c, h2, (size_t)nv, dist);
       k_multiaxpy<<<gd, kBlock, 0, c->stream>>>(N, w, c->V, N, nv, h2, -1.0);
       dot(c, Nd, w, w, h2 + nv, dist);
       k_scale_by_inv<<<gd, kBlock, 0, c->stream>>>(N, w, h2 + nv, 1, w);
@@ -1523,6 +1592,15 @@ static int prepare_amg(fdal_ctx *c, Amg &g, bool dist) {
   int st;
   const int nl = (int)g.lev.size();
   g.dist = dist;
+  if (!dist)
+    g.rep_from = 0;
+  else if (g.rep_from < 0)
+    g.rep_from = nl - 1;  // only the coarsest operator is replicated
+  if (dist && (g.rep_from < 1 || g.rep_from > nl - 1)) {
+    set_err(c, "a partitioned AMG hierarchy needs at least one partitioned and one replicated level (replicated from %d of %d)",
+            g.rep_from, nl);
+    return FDAL_ERR_INVALID;
+  }
   for (int l = 0; l < nl; ++l) {
     AmgLevel &L = g.lev[l];
     if (!L.hA.set) {
@@ -1530,40 +1608,60 @@ static int prepare_amg(fdal_ctx *c, Amg &g, bool dist) {
       return FDAL_ERR_STATE;
     }
     const bool coarsest = (l == nl - 1);
-    if (coarsest) {
-      g.cn_global = (int)L.hA.nr;
-      if (!dist || g.c_hi < 0) {
-        g.c_lo = 0;
-        g.c_hi = L.hA.nr;
+    const bool part = dist && l < g.rep_from;  // this level's rows are a partition
+    if (L.hA.owned_cols() != L.hA.nr) {
+      set_err(c, "AMG level %d: A is %lld x %lld (owned columns), must be square", l, (long long)L.hA.nr,
+              (long long)L.hA.owned_cols());
+      return FDAL_ERR_SHAPE;
+    }
+    if (!coarsest && (L.degree < 1 || !(L.lmax > 0.0) || !(L.ratio > 1.0))) {
+      set_err(c, "AMG level %d: Chebyshev needs degree >= 1, lambda_max > 0, eig_ratio > 1 (got %d, %g, %g)", l, L.degree,
+              L.lmax, L.ratio);
+      return FDAL_ERR_INVALID;
+    }
+    if (coarsest) g.cn_global = (int)L.hA.nr;
+    L.n = (int)L.hA.nr;
+    if (dist && l == g.rep_from) {
+      if (g.c_hi < 0) {
+        set_err(c, "fdal_amg_set_coarse_range was not called for the first replicated level");
+        return FDAL_ERR_STATE;
       }
-      L.n = (int)(g.c_hi - g.c_lo);
-    } else {
-      L.n = (int)L.hA.nr;
+      if (g.c_lo < 0 || g.c_hi < g.c_lo || g.c_hi > L.hA.nr) {
+        set_err(c, "AMG level %d: owned range [%lld, %lld) outside [0, %lld]", l, (long long)g.c_lo, (long long)g.c_hi,
+                (long long)L.hA.nr);
+        return FDAL_ERR_SHAPE;
+      }
     }
     if ((st = upload_csr(c, L.hA, L.A, (l == 0 && !coarsest && &g == &c->amg[0]) ? c->cfg.block_size : 1))) return st;
-    L.A.dist_rows = dist;
+    L.A.dist_rows = part;
     if (!coarsest) {
       if (!L.hP.set) {
         set_err(c, "AMG level %d has no prolongator", l);
         return FDAL_ERR_STATE;
       }
       const AmgLevel &Nx = g.lev[l + 1];
-      const int64_t next_rows = (l + 1 == nl - 1 && dist && g.c_hi >= 0) ? (g.c_hi - g.c_lo) : Nx.hA.nr;
-      if (L.hP.owned_cols() != next_rows) {
-        set_err(c, "AMG level %d: P has %lld owned columns, next level has %lld rows", l,
-                (long long)L.hP.owned_cols(), (long long)next_rows);
+      if (L.hP.nr != L.hA.nr || L.hP.owned_cols() != Nx.hA.nr) {
+        set_err(c, "AMG level %d: P is %lld x %lld (owned columns), expected %lld x %lld", l, (long long)L.hP.nr,
+                (long long)L.hP.owned_cols(), (long long)L.hA.nr, (long long)Nx.hA.nr);
         return FDAL_ERR_SHAPE;
       }
       if ((st = upload_csr(c, L.hP, L.P))) return st;
       if (!L.hR.set) {
-        if (dist) {
+        if (part) {
           set_err(c, "AMG level %d: a partitioned hierarchy needs an explicit R with its halo plan", l);
           return FDAL_ERR_STATE;
         }
         host_transpose(L.hP, L.hR);
       }
+      const int64_t r_rows = (dist && l + 1 == g.rep_from) ? (g.c_hi - g.c_lo) : Nx.hA.nr;
+      if (L.hR.nr != r_rows || L.hR.owned_cols() != L.hA.nr) {
+        set_err(c, "AMG level %d: R is %lld x %lld (owned columns), expected %lld x %lld", l, (long long)L.hR.nr,
+                (long long)L.hR.owned_cols(), (long long)r_rows, (long long)L.hA.nr);
+        return FDAL_ERR_SHAPE;
+      }
       if ((st = upload_csr(c, L.hR, L.R))) return st;
-      L.P.dist_rows = L.R.dist_rows = dist;
+      L.P.dist_rows = part;
+      L.R.dist_rows = part && l + 1 < g.rep_from;
       if ((st = dvec(c, &L.invd, L.n))) return st;
       if (!L.h_invd.empty()) {
         CU(cudaMemcpyAsync(L.invd, L.h_invd.data(), (size_t)L.n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
@@ -1585,9 +1683,214 @@ static int prepare_amg(fdal_ctx *c, Amg &g, bool dist) {
     L.hP = HostCsr();
     L.hR = HostCsr();
   }
-  if (dist && (st = dvec(c, &g.cfull, g.cn_global))) return st;
+  if (dist) {
+    if ((st = dvec(c, &g.rown, g.c_hi - g.c_lo))) return st;
+    if (c->p2p) {
+      // all-gather channel of the first replicated level: rank q's rows land at its offset
+      // (the peers' offsets are exchanged in comm_build)
+      Chan ch;
+      ch.bcast = true;
+      ch.cap = g.lev[(size_t)g.rep_from].n;
+      ch.src_off.assign((size_t)c->nranks, -1);
+      ch.src_off[(size_t)c->rank] = g.c_lo;
+      for (int q = 0; q < c->nranks; ++q) ch.nb.push_back(q);
+      g.gather_chan = (int)c->chans.size();
+      c->chans.push_back(ch);
+    }
+  }
   if ((st = invert_coarse(c, g))) return st;
   g.ready = true;
+  return FDAL_OK;
+}
+
+// ------------------------------------------------------------------ peer channels (setup)
+static bool nccl_ok(ncclResult_t r) { return r == ncclSuccess; }
+// all-gather `words` int64 per rank through NCCL (setup only)
+static int gather_table(fdal_ctx *c, const std::vector<long long> &mine, std::vector<long long> &all) {
+  const size_t W = mine.size();
+  long long *d = nullptr;
+  CU(cudaMalloc((void **)&d, W * (size_t)c->nranks * sizeof(long long)));
+  CU(cudaMemcpyAsync(d + W * (size_t)c->rank, mine.data(), W * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+  if (!nccl_ok(nccl_api()->AllGather(d + W * (size_t)c->rank, d, W, ncclInt64, c->comm, c->stream))) {
+    cudaFree(d);
+    set_err(c, "ncclAllGather failed during channel setup");
+    return FDAL_ERR_NCCL;
+  }
+  all.resize(W * (size_t)c->nranks);
+  CU(cudaMemcpyAsync(all.data(), d, all.size() * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  cudaFree(d);
+  return FDAL_OK;
+}
+// can every rank map every other rank's memory?  (decided once, before anything is uploaded;
+// all ranks take the same decision)
+static int probe_peer_access(fdal_ctx *c, bool *ok_out) {
+  *ok_out = false;
+  char *buf = nullptr;
+  CU(cudaMalloc((void **)&buf, 4096));
+  cudaIpcMemHandle_t h;
+  bool ok = cudaIpcGetMemHandle(&h, buf) == cudaSuccess;
+  std::vector<long long> mine(9, 0), all;
+  memcpy(mine.data(), &h, sizeof(h));
+  mine[8] = ok ? 1 : 0;
+  int st = gather_table(c, mine, all);
+  if (st) {
+    cudaFree(buf);
+    return st;
+  }
+  std::vector<void *> opened;
+  for (int q = 0; q < c->nranks && ok; ++q) {
+    if (!all[(size_t)q * 9 + 8]) ok = false;
+    if (q == c->rank || !ok) continue;
+    cudaIpcMemHandle_t hq;
+    memcpy(&hq, &all[(size_t)q * 9], sizeof(hq));
+    void *p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, hq, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      ok = false;
+      cudaGetLastError();
+    } else {
+      opened.push_back(p);
+    }
+  }
+  for (void *p : opened) cudaIpcCloseMemHandle(p);
+  // agreement: one more round
+  mine.assign(9, 0);
+  mine[8] = ok ? 1 : 0;
+  st = gather_table(c, mine, all);
+  cudaFree(buf);
+  if (st) return st;
+  for (int q = 0; q < c->nranks; ++q) ok = ok && all[(size_t)q * 9 + 8];
+  *ok_out = ok;
+  return FDAL_OK;
+}
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+// allocate the arena, exchange layouts + IPC handles, map the peers, build the device views
+static int comm_build(fdal_ctx *c) {
+  if (!c->p2p) return FDAL_OK;
+  const int nr = c->nranks;
+  const size_t nch = c->chans.size();
+  size_t off = 0;
+  for (Chan &ch : c->chans) {
+    ch.recv_off = off;
+    off += align256((size_t)2 * std::max(ch.cap, 1) * sizeof(double));
+    ch.flags_off = off;
+    off += align256((size_t)nr * sizeof(unsigned long long));
+    ch.misc_off = off;
+    off += 256;  // epoch (8 B) at +0, push counter (4 B) at +128
+  }
+  c->arena_bytes = std::max<size_t>(off, 256);
+  CU(cudaMalloc((void **)&c->arena, c->arena_bytes));
+  CU(cudaMemsetAsync(c->arena, 0, c->arena_bytes, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, c->arena));
+  const size_t per = 3 + (size_t)nr, W = 8 + 1 + nch * per;
+  std::vector<long long> mine(W, 0), all;
+  memcpy(mine.data(), &h, sizeof(h));
+  mine[8] = (long long)nch;
+  for (size_t i = 0; i < nch; ++i) {
+    const Chan &ch = c->chans[i];
+    long long *t = &mine[9 + i * per];
+    t[0] = (long long)ch.recv_off;
+    t[1] = (long long)ch.flags_off;
+    t[2] = ch.cap;
+    for (int q = 0; q < nr; ++q) t[3 + q] = ch.src_off[(size_t)q];
+  }
+  // the channel count must agree before tables of that size are exchanged
+  {
+    std::vector<long long> cnt(1, (long long)nch), cnts;
+    int st = gather_table(c, cnt, cnts);
+    if (st) return st;
+    for (int q = 0; q < nr; ++q)
+      if (cnts[(size_t)q] != (long long)nch) {
+        set_err(c, "rank %d registered %lld exchange channels, rank %d has %zu: the ranks were set up differently", q,
+                cnts[(size_t)q], c->rank, nch);
+        return FDAL_ERR_STATE;
+      }
+  }
+  int st = gather_table(c, mine, all);
+  if (st) return st;
+  c->peer_arena.assign((size_t)nr, nullptr);
+  c->peer_arena[(size_t)c->rank] = c->arena;
+  for (int q = 0; q < nr; ++q) {
+    if (q == c->rank) continue;
+    cudaIpcMemHandle_t hq;
+    memcpy(&hq, &all[(size_t)q * W], sizeof(hq));
+    void *p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, hq, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      set_err(c, "cudaIpcOpenMemHandle(rank %d) failed: %s (set FDAL_COMM=nccl for the NCCL fallback)", q,
+              cudaGetErrorString(e));
+      return FDAL_ERR_CUDA;
+    }
+    c->peer_arena[(size_t)q] = (char *)p;
+  }
+  auto T = [&](int q, size_t i) { return &all[(size_t)q * W + 9 + i * per]; };
+  // one device blob with every channel's neighbour tables
+  std::vector<char> blob;
+  auto put = [&](const void *src, size_t bytes) {
+    const size_t o = align256(blob.size());
+    blob.resize(o + bytes);
+    if (bytes) memcpy(blob.data() + o, src, bytes);
+    return o;
+  };
+  struct Offs {
+    size_t rank, recv, cap, flag, begin;
+  };
+  std::vector<Offs> offs(nch);
+  for (size_t i = 0; i < nch; ++i) {
+    Chan &ch = c->chans[i];
+    const int nnb = (int)ch.nb.size();
+    std::vector<double *> nrecv((size_t)nnb);
+    std::vector<int> ncap((size_t)nnb);
+    std::vector<unsigned long long *> nflag((size_t)nnb);
+    for (int k = 0; k < nnb; ++k) {
+      const int q = ch.nb[(size_t)k];
+      const long long *t = T(q, i);
+      // where MY entries start inside q's slot
+      const long long o = ch.bcast ? ch.src_off[(size_t)c->rank] : t[3 + c->rank];
+      if (ch.bcast && (t[2] != ch.cap)) {
+        set_err(c, "exchange channel %zu: rank %d has capacity %lld, rank %d has %d", i, q, t[2], c->rank, ch.cap);
+        return FDAL_ERR_SHAPE;
+      }
+      nrecv[(size_t)k] = (double *)(c->peer_arena[(size_t)q] + t[0]) + std::max<long long>(o, 0);
+      ncap[(size_t)k] = (int)t[2];
+      nflag[(size_t)k] = (unsigned long long *)(c->peer_arena[(size_t)q] + t[1]) + c->rank;
+    }
+    if (ch.nb_begin.empty()) ch.nb_begin.assign((size_t)nnb + 1, 0);
+    offs[i].rank = put(ch.nb.data(), (size_t)nnb * sizeof(int));
+    offs[i].recv = put(nrecv.data(), (size_t)nnb * sizeof(double *));
+    offs[i].cap = put(ncap.data(), (size_t)nnb * sizeof(int));
+    offs[i].flag = put(nflag.data(), (size_t)nnb * sizeof(unsigned long long *));
+    offs[i].begin = put(ch.nb_begin.data(), ch.nb_begin.size() * sizeof(int));
+  }
+  const size_t views_off = align256(blob.size());
+  blob.resize(views_off + nch * sizeof(ChanDev));
+  char *dblob = nullptr;
+  if ((st = dmalloc(c, &dblob, blob.size()))) return st;
+  for (size_t i = 0; i < nch; ++i) {
+    Chan &ch = c->chans[i];
+    ch.d.recv = (double *)(c->arena + ch.recv_off);
+    ch.d.flags = (unsigned long long *)(c->arena + ch.flags_off);
+    ch.d.epoch = (unsigned long long *)(c->arena + ch.misc_off);
+    ch.d.counter = (unsigned int *)(c->arena + ch.misc_off + 128);
+    ch.d.cap = ch.cap;
+    ch.d.nnb = (int)ch.nb.size();
+    ch.d.nb_rank = (const int *)(dblob + offs[i].rank);
+    ch.d.nb_recv = (double *const *)(dblob + offs[i].recv);
+    ch.d.nb_cap = (const int *)(dblob + offs[i].cap);
+    ch.d.nb_flag = (unsigned long long *const *)(dblob + offs[i].flag);
+    ch.d.nb_begin = (const int *)(dblob + offs[i].begin);
+    ch.d_dev = (ChanDev *)(dblob + views_off) + i;
+    memcpy(blob.data() + views_off + i * sizeof(ChanDev), &ch.d, sizeof(ChanDev));
+  }
+  CU(cudaMemcpyAsync(dblob, blob.data(), blob.size(), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  // nobody may push before every rank has zeroed and mapped everything: one more collective
+  {
+    std::vector<long long> one(1, 1), ones;
+    if ((st = gather_table(c, one, ones))) return st;
+  }
   return FDAL_OK;
 }
 
@@ -1656,11 +1959,8 @@ int fdal_create(fdal_ctx **out, const fdal_config *cfg) {
   }
   if (const char *e = getenv("FDAL_OVERLAP")) c->overlap_mass = atoi(e) != 0;
   // tuning knobs (measurement only; defaults are the shipped configuration)
-  if (const char *e = getenv("FDAL_SPMV")) c->prefer_stream = strcmp(e, "stream") == 0;
   if (const char *e = getenv("FDAL_UNROLL")) c->spmv_unroll = atoi(e);
-  if (const char *e = getenv("FDAL_BSR_UNROLL")) c->bsr_unroll = atoi(e);
-  if (const char *e = getenv("FDAL_SPMV_PF")) c->spmv_prefetch = atoi(e) > 0;
-  if (const char *e = getenv("FDAL_STREAM_CTAS")) c->stream_ctas_per_sm = std::max(1, atoi(e));
+  if (const char *e = getenv("FDAL_BSR_UNROLL")) c->bsr_unroll2 = c->bsr_unroll3 = atoi(e);
   *out = c;
   return FDAL_OK;
 }
@@ -1674,6 +1974,9 @@ void fdal_destroy(fdal_ctx *c) {
     if (w->fixed_exec) cudaGraphExecDestroy(w->fixed_exec);
   }
   for (void *p : c->allocs) cudaFree(p);
+  for (int q = 0; q < (int)c->peer_arena.size(); ++q)
+    if (q != c->rank && c->peer_arena[(size_t)q]) cudaIpcCloseMemHandle(c->peer_arena[(size_t)q]);
+  if (c->arena) cudaFree(c->arena);
   if (c->comm) nccl_api()->CommDestroy(c->comm);
   if (c->h_scal) cudaFreeHost(c->h_scal);
   if (c->stream2) cudaStreamDestroy(c->stream2);
@@ -1685,47 +1988,88 @@ void fdal_destroy(fdal_ctx *c) {
 
 const char *fdal_last_error(const fdal_ctx *c) { return c ? c->err.c_str() : "null context"; }
 
-int fdal_set_csr(fdal_ctx *c, int id, int64_t nr, int64_t nc, int64_t nnz, const int64_t *rp, const int32_t *ci,
-                 const double *v) {
-  CHECK_CTX(c);
-  if (id < 0 || id >= FDAL_MAT_COUNT || !rp || nr < 0 || nc < 0 || nnz < 0 || (nnz && (!ci || !v))) {
-    set_err(c, "fdal_set_csr: bad argument");
+#define NOT_FINAL(c)                                                                                            \
+  if ((c)->finalized || !(c)->allocs.empty()) {                                                                 \
+    set_err((c), "the context is already finalized: setters are refused (destroy it and create a new one)");    \
+    return FDAL_ERR_STATE;                                                                                      \
+  }
+// row_ptr / column checks shared by every CSR entry point
+static int check_csr(fdal_ctx *c, const char *what, int64_t nr, int64_t nc, int64_t nnz, const int64_t *rp,
+                     const int32_t *ci, const double *v) {
+  if (!rp || nr < 0 || nc < 0 || nnz < 0 || (nnz && (!ci || !v))) {
+    set_err(c, "%s: bad argument", what);
     return FDAL_ERR_INVALID;
   }
   if (rp[0] != 0 || rp[nr] != nnz) {
-    set_err(c, "matrix %d: row_ptr inconsistent with nnz", id);
+    set_err(c, "%s: row_ptr inconsistent with nnz", what);
     return FDAL_ERR_SHAPE;
   }
-  if (nnz >= (int64_t)std::numeric_limits<int>::max()) {
-    set_err(c, "matrix %d: %lld nnz exceeds the 32-bit row_ptr of this build", id, (long long)nnz);
+  if (nnz >= (int64_t)std::numeric_limits<int>::max() || nr >= (int64_t)std::numeric_limits<int>::max()) {
+    set_err(c, "%s: %lld nnz / %lld rows exceed the 32-bit row_ptr of this build", what, (long long)nnz, (long long)nr);
     return FDAL_ERR_UNSUPPORTED;
   }
-  HostCsr &h = c->hmat[id];
+  int bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad)
+  for (int64_t i = 0; i < nr; ++i) {
+    if (rp[i + 1] < rp[i]) {
+      bad |= 1;
+      continue;
+    }
+    if (rp[i] < 0 || rp[i + 1] > nnz) {
+      bad |= 1;
+      continue;
+    }
+    for (int64_t k = rp[i]; k < rp[i + 1]; ++k)
+      if (ci[k] < 0 || ci[k] >= nc) bad |= 2;
+  }
+  if (bad & 1) {
+    set_err(c, "%s: row_ptr not monotone", what);
+    return FDAL_ERR_SHAPE;
+  }
+  if (bad & 2) {
+    set_err(c, "%s: column index out of range", what);
+    return FDAL_ERR_SHAPE;
+  }
+  return FDAL_OK;
+}
+static void fill_host_csr(HostCsr &h, int64_t nr, int64_t nc, int64_t nnz, const int64_t *rp, const int32_t *ci,
+                          const double *v) {
+  h = HostCsr();
   h.nr = nr;
   h.nc = nc;
   h.nnz = nnz;
   h.rp.resize((size_t)nr + 1);
-  for (int64_t i = 0; i <= nr; ++i) {
-    if (i && rp[i] < rp[i - 1]) {
-      set_err(c, "matrix %d: row_ptr not monotone", id);
-      return FDAL_ERR_SHAPE;
-    }
-    h.rp[(size_t)i] = (int)rp[i];
+  h.ci.resize((size_t)nnz);
+  h.v.resize((size_t)nnz);
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i <= nr; ++i) h.rp[(size_t)i] = (int)rp[i];
+#pragma omp parallel for schedule(static)
+  for (int64_t k = 0; k < nnz; ++k) {
+    h.ci[(size_t)k] = ci[k];
+    h.v[(size_t)k] = v[k];
   }
-  h.ci.assign(ci, ci + nnz);
-  h.v.assign(v, v + nnz);
-  for (int64_t k = 0; k < nnz; ++k)
-    if (ci[k] < 0 || ci[k] >= nc) {
-      set_err(c, "matrix %d: column index out of range", id);
-      return FDAL_ERR_SHAPE;
-    }
   h.set = true;
-  c->finalized = false;
+}
+
+int fdal_set_csr(fdal_ctx *c, int id, int64_t nr, int64_t nc, int64_t nnz, const int64_t *rp, const int32_t *ci,
+                 const double *v) {
+  CHECK_CTX(c);
+  NOT_FINAL(c);
+  if (id < 0 || id >= FDAL_MAT_COUNT) {
+    set_err(c, "fdal_set_csr: bad matrix id %d", id);
+    return FDAL_ERR_INVALID;
+  }
+  char what[32];
+  snprintf(what, sizeof(what), "matrix %d", id);
+  int st = check_csr(c, what, nr, nc, nnz, rp, ci, v);
+  if (st) return st;
+  fill_host_csr(c->hmat[id], nr, nc, nnz, rp, ci, v);
   return FDAL_OK;
 }
 
 int fdal_set_diag(fdal_ctx *c, int id, int64_t n, const double *d) {
   CHECK_CTX(c);
+  NOT_FINAL(c);
   if (!d || n < 0) return FDAL_ERR_INVALID;
   if (id == FDAL_DIAG_W_INV)
     c->h_winv.assign(d, d + n);
@@ -1733,47 +2077,46 @@ int fdal_set_diag(fdal_ctx *c, int id, int64_t n, const double *d) {
     c->h_mp_lumped.assign(d, d + n);
   else
     return FDAL_ERR_INVALID;
-  c->finalized = false;
   return FDAL_OK;
 }
 
-static void copy_view(const fdal_csr_view *v, HostCsr &h) {
-  h.nr = v->n_rows;
-  h.nc = v->n_cols;
-  h.nnz = v->nnz;
-  h.rp.resize((size_t)v->n_rows + 1);
-  for (int64_t i = 0; i <= v->n_rows; ++i) h.rp[(size_t)i] = (int)v->row_ptr[i];
-  h.ci.assign(v->col, v->col + v->nnz);
-  h.v.assign(v->val, v->val + v->nnz);
-  h.set = true;
+static int copy_view(fdal_ctx *c, const char *what, const fdal_csr_view *v, HostCsr &h) {
+  int st = check_csr(c, what, v->n_rows, v->n_cols, v->nnz, v->row_ptr, v->col, v->val);
+  if (st) return st;
+  fill_host_csr(h, v->n_rows, v->n_cols, v->nnz, v->row_ptr, v->col, v->val);
+  return FDAL_OK;
 }
 int fdal_amg_set_level(fdal_ctx *c, int which, int level, const fdal_csr_view *A, const fdal_csr_view *P,
                        const fdal_csr_view *R, const double *inv_diag, double lmax, int degree, double ratio) {
   CHECK_CTX(c);
+  NOT_FINAL(c);
   if (which < 0 || which > 1 || level < 0 || level > 30 || !A) return FDAL_ERR_INVALID;
-  if (A->nnz >= (int64_t)std::numeric_limits<int>::max()) return FDAL_ERR_UNSUPPORTED;
   Amg &g = c->amg[which];
-  if (g.ready) {
-    set_err(c, "AMG hierarchy %d already finalized", which);
-    return FDAL_ERR_STATE;
-  }
   if ((int)g.lev.size() < level + 1) g.lev.resize(level + 1);
   AmgLevel &L = g.lev[level];
-  copy_view(A, L.hA);
+  char what[48];
+  int st;
+  snprintf(what, sizeof(what), "AMG %d level %d A", which, level);
+  if ((st = copy_view(c, what, A, L.hA))) return st;
+  L.hP = HostCsr();
+  L.hR = HostCsr();
   if (P) {
     if (P->n_rows != A->n_rows) {
       set_err(c, "AMG level %d: P has %lld rows, A has %lld", level, (long long)P->n_rows, (long long)A->n_rows);
       return FDAL_ERR_SHAPE;
     }
-    copy_view(P, L.hP);
+    snprintf(what, sizeof(what), "AMG %d level %d P", which, level);
+    if ((st = copy_view(c, what, P, L.hP))) return st;
   }
-  if (R) copy_view(R, L.hR);
+  if (R) {
+    snprintf(what, sizeof(what), "AMG %d level %d R", which, level);
+    if ((st = copy_view(c, what, R, L.hR))) return st;
+  }
   L.h_invd.clear();
   if (inv_diag) L.h_invd.assign(inv_diag, inv_diag + A->n_rows);
   L.lmax = lmax;
   L.degree = degree;
   L.ratio = ratio;
-  c->finalized = false;
   return FDAL_OK;
 }
 int fdal_amg_set_coarse(fdal_ctx *c, int which, int level, const fdal_csr_view *A) {
@@ -1843,6 +2186,20 @@ int fdal_finalize(fdal_ctx *c) {
   if ((st = dvec(c, &c->d_scal, 512))) return st;
   CU(cudaMallocHost((void **)&c->h_scal, 512 * sizeof(double)));
 
+  if (c->p2p) {
+    c->vec_cap = (int)std::max<int64_t>(c->m, 1);
+    for (int which = 0; which < 2; ++which) {
+      Chan ch;
+      ch.bcast = true;
+      const int region = which == 0 ? kArCap : c->vec_cap;
+      ch.cap = region * c->nranks;
+      ch.src_off.assign((size_t)c->nranks, -1);
+      ch.src_off[(size_t)c->rank] = (int64_t)region * c->rank;
+      for (int q = 0; q < c->nranks; ++q) ch.nb.push_back(q);
+      (which == 0 ? c->ch_scalar : c->ch_vec) = (int)c->chans.size();
+      c->chans.push_back(ch);
+    }
+  }
   // explicit transposes (gather kernels only: no atomics, deterministic)
   if (!c->hmat[FDAL_MAT_C].set) host_transpose(c->hmat[FDAL_MAT_CT], c->hmat[FDAL_MAT_C]);
   if (is_stokes(c) && !c->hmat[FDAL_MAT_B].set) host_transpose(c->hmat[FDAL_MAT_BT], c->hmat[FDAL_MAT_B]);
@@ -1856,6 +2213,24 @@ int fdal_finalize(fdal_ctx *c) {
       std::vector<int>().swap(h.rp);
     }
   for (int id : {FDAL_MAT_A, FDAL_MAT_BT, FDAL_MAT_B, FDAL_MAT_MP}) c->dmat[id].dist_rows = D;
+  // AMG
+  if (c->cfg.inner_prec == FDAL_PREC_AMG) {
+    for (int a = 0; a < 2; ++a) {
+      if (a == 1 && !is_elliptic(c)) continue;
+      if (c->amg[a].lev.empty()) {
+        set_err(c, "AMG hierarchy %d not set", a);
+        return FDAL_ERR_STATE;
+      }
+      if (c->amg[a].lev.size() > 1 && c->amg[a].lev[0].hA.nr != (a == 0 ? c->n0 : c->n1)) {
+        set_err(c, "AMG hierarchy %d: fine level has %lld rows, block has %lld", a,
+                (long long)c->amg[a].lev[0].hA.nr, (long long)(a == 0 ? c->n0 : c->n1));
+        return FDAL_ERR_SHAPE;
+      }
+      if ((st = prepare_amg(c, c->amg[a], a == 0 && c->nranks > 1))) return st;
+    }
+  }
+  // peer channels: everything that exchanges data has been registered by now
+  if ((st = comm_build(c))) return st;
   // dots: the replicated tail blocks are counted on rank 0 only
   {
     const int64_t tail = k == FDAL_KIND_LAPLACE ? c->n1 : is_stokes(c) ? c->n2 : c->n1 + c->n2;
@@ -1893,9 +2268,14 @@ int fdal_finalize(fdal_ctx *c) {
     if ((st = invdiag_of(c, c->dmat[FDAL_MAT_M], &c->d_m_invdiag))) return st;
     if ((st = mass_calibrate(c, c->cgmass_m, c->dmat[FDAL_MAT_M], c->d_m_invdiag, &c->mass_its_m))) return st;
     static const bool no_cta = getenv("FDAL_NO_MASS_CTA") != nullptr;
-    if (c->m <= kMassCtaMaxRows && !no_cta && (st = dvec(c, &c->mass_cta_ws, 5 * c->m))) return st;
-    if (const char *e = getenv("FDAL_DENSE_WINV"))
-      if (atoi(e) > 0 && c->m > 0 && c->m <= kDenseWinvMaxRows && (st = build_dense_winv(c))) return st;
+    if (c->m <= kMassCtaMaxRows && !no_cta) {
+      if ((st = dvec(c, &c->mass_cta_ws, 5 * c->m))) return st;
+      CU(cudaFuncSetAttribute(k_mass_pcg_cta<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)(4 * kMassCtaSmemRows * sizeof(double))));
+    }
+    // small multiplier spaces: the exact W^-1 as ONE L2-resident dense GEMV (FDAL_DENSE_WINV=0: keep the PCG)
+    const char *dw = getenv("FDAL_DENSE_WINV");
+    if ((!dw || atoi(dw) > 0) && c->m > 0 && c->m <= kDenseWinvMaxRows && (st = build_dense_winv(c))) return st;
   }
   if (is_stokes(c)) {
     if ((st = alloc_cg(c, c->cgmass_p, c->n1))) return st;
@@ -1915,22 +2295,6 @@ int fdal_finalize(fdal_ctx *c) {
         spmv(c, c->dmat[FDAL_MAT_MP], c->t_p0, EpiAssign{c->d_mp_lumped, 1.0});
         k_reciprocal<<<grid_elems(c, c->n1), kBlock, 0, c->stream>>>(c->n1, c->d_mp_lumped);
       }
-    }
-  }
-  // AMG
-  if (c->cfg.inner_prec == FDAL_PREC_AMG) {
-    for (int a = 0; a < 2; ++a) {
-      if (a == 1 && !is_elliptic(c)) continue;
-      if (c->amg[a].lev.empty()) {
-        set_err(c, "AMG hierarchy %d not set", a);
-        return FDAL_ERR_STATE;
-      }
-      if (c->amg[a].lev.size() > 1 && c->amg[a].lev[0].hA.nr != (a == 0 ? c->n0 : c->n1)) {
-        set_err(c, "AMG hierarchy %d: fine level has %lld rows, block has %lld", a,
-                (long long)c->amg[a].lev[0].hA.nr, (long long)(a == 0 ? c->n0 : c->n1));
-        return FDAL_ERR_SHAPE;
-      }
-      if ((st = prepare_amg(c, c->amg[a], a == 0 && c->nranks > 1))) return st;
     }
   }
   // outer Krylov workspace
@@ -2288,11 +2652,26 @@ int fdal_comm_init(fdal_ctx *c, const char id[128], int rank, int n_ranks) {
     set_err(c, "ncclCommInitRank failed: %s", n->GetErrorString ? n->GetErrorString(r) : "?");
     return FDAL_ERR_NCCL;
   }
+  // per-iteration traffic goes through peer-mapped channels unless the ranks cannot map each
+  // other's memory (or FDAL_COMM=nccl asks for the NCCL send/recv + all-reduce fallback)
+  const char *mode = getenv("FDAL_COMM");
+  if (!(mode && strcmp(mode, "nccl") == 0)) {
+    bool ok = false;
+    int st = probe_peer_access(c, &ok);
+    if (st) return st;
+    c->p2p = ok;
+    if (!ok && mode && strcmp(mode, "p2p") == 0) {
+      set_err(c, "FDAL_COMM=p2p but the ranks cannot map each other's memory (cudaIpc)");
+      return FDAL_ERR_UNSUPPORTED;
+    }
+  }
   return FDAL_OK;
 }
+int fdal_comm_mode(const fdal_ctx *c) { return c ? (c->nranks <= 1 ? 0 : (c->p2p ? 2 : 1)) : -1; }
 int fdal_set_halo(fdal_ctx *c, int matrix_id, int level, int which, int64_t n_owned_cols, int64_t n_halo,
                   const int32_t *send_counts, const int32_t *send_idx, const int32_t *recv_counts) {
   CHECK_CTX(c);
+  NOT_FINAL(c);
   if (!send_counts || !recv_counts || n_owned_cols < 0 || n_halo < 0) return FDAL_ERR_INVALID;
   HostCsr *h = nullptr;
   if (matrix_id >= 0 && matrix_id < FDAL_MAT_COUNT) {
@@ -2335,9 +2714,17 @@ int fdal_set_halo(fdal_ctx *c, int matrix_id, int level, int which, int64_t n_ow
 }
 int fdal_amg_set_coarse_range(fdal_ctx *c, int which, int64_t lo, int64_t hi) {
   CHECK_CTX(c);
+  NOT_FINAL(c);
   if (which < 0 || which > 1 || lo < 0 || hi < lo) return FDAL_ERR_INVALID;
   c->amg[which].c_lo = lo;
   c->amg[which].c_hi = hi;
+  return FDAL_OK;
+}
+int fdal_amg_set_replicated_from(fdal_ctx *c, int which, int level) {
+  CHECK_CTX(c);
+  NOT_FINAL(c);
+  if (which < 0 || which > 1 || level < 1) return FDAL_ERR_INVALID;
+  c->amg[which].rep_from = level;
   return FDAL_OK;
 }
 

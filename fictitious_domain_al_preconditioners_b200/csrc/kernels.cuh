@@ -36,20 +36,92 @@ struct CsrDev {
 
 // x vector with an optional halo part (multi-GPU): columns [0,n_owned) are local,
 // [n_owned, ...) index the halo receive buffer of the matrix.
+//
+// Multi-GPU exchange channels (one process per GPU, peers mapped with cudaIpc over NVLink):
+// a channel is a local receive buffer with two slots (epoch parity), one flag word per
+// source rank and a device-resident epoch counter.  A sender stores its entries DIRECTLY
+// into the receivers' slot (e & 1) with ordinary global stores through the peer mapping,
+// fences at system scope and then releases flag[me] = e on every neighbour; a consumer
+// acquires flag[q] >= e for all its neighbours before it touches the slot.  The neighbour
+// relation is symmetric by construction and every rank issues the same sequence of
+// exchanges per channel, so "q released epoch e+1" implies "q is done reading epoch e":
+// two slots suffice and no acknowledgement traffic is needed.  Nothing here depends on a
+// host-supplied value, so the kernels replay unchanged inside CUDA graphs.
+struct ChanDev {
+  double *recv = nullptr;                 // local [2][cap]
+  unsigned long long *flags = nullptr;    // local [nranks], written by the peers
+  unsigned long long *epoch = nullptr;    // local device scalar: last completed push
+  unsigned int *counter = nullptr;        // last-block election of the push kernel
+  int cap = 0;                            // doubles per slot
+  int nnb = 0;                            // neighbours (for broadcast channels: all ranks incl. self)
+  const int *nb_rank = nullptr;           // [nnb]
+  double *const *nb_recv = nullptr;       // [nnb] peer slot-0 address where MY entries start
+  const int *nb_cap = nullptr;            // [nnb] the peer's slot stride
+  unsigned long long *const *nb_flag = nullptr;  // [nnb] &peer.flags[me]
+  const int *nb_begin = nullptr;          // [nnb + 1] my send-list range per neighbour (gather channels)
+};
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// all threads of the block call this; returns once every neighbour has released epoch >= e
+__device__ __forceinline__ void chan_wait(const ChanDev &ch, unsigned long long e) {
+  for (int k = threadIdx.x; k < ch.nnb; k += blockDim.x) {
+    const unsigned long long *f = ch.flags + ch.nb_rank[k];
+    while (ld_acquire_sys(f) < e) __nanosleep(20);
+  }
+  __syncthreads();
+}
+
 struct XVec {
   const double *x;
   const double *halo;
   int n_owned;
+  // multi-GPU with peer channels: halo = ch->recv + (epoch & 1) * cap, rows are walked in
+  // `order` (interior chunks first) and a block acquires the halo before its first chunk
+  // at position >= n_interior.  ch == nullptr: single GPU or NCCL-filled halo buffer.
+  const ChanDev *ch = nullptr;
+  const int *order = nullptr;
+  int n_interior = 0;
 };
 __device__ __forceinline__ double xload(const XVec &X, int c) {
-  return c < X.n_owned ? __ldg(X.x + c) : __ldg(X.halo + (c - X.n_owned));
+  return c < X.n_owned ? __ldg(X.x + c) : X.halo[c - X.n_owned];
+}
+// per-block state of a halo consumer
+struct HaloState {
+  unsigned long long e = 0;
+  bool armed = false, done = false;
+};
+__device__ __forceinline__ void halo_begin(XVec &X, HaloState &h) {
+  if (X.ch) {
+    h.e = *X.ch->epoch;  // written by the push kernel that precedes this kernel in stream order
+    X.halo = X.ch->recv + (size_t)(h.e & 1ull) * X.ch->cap;
+    h.armed = true;
+  }
+}
+// p: chunk position (block-uniform).  Returns the chunk to process.
+__device__ __forceinline__ long long halo_chunk(const XVec &X, HaloState &h, long long p) {
+  if (h.armed && !h.done && p >= X.n_interior) {
+    chan_wait(*X.ch, h.e);
+    h.done = true;
+  }
+  return X.order ? (long long)__ldg(X.order + p) : p;
 }
 
 // ---- in-kernel reduction: block partial -> last block sums partials in fixed order
+constexpr int kArCap = 128;  // doubles per rank and slot in the scalar all-reduce channel
 struct Reducer {
   double *partials;       // [gridDim.x * n_out]
   unsigned int *counter;  // self-resetting (atomicInc wrap)
   double *out;            // [n_out] device scalars
+  // multi-GPU: the block that finishes the reduction also sums out[] over the ranks through
+  // the scalar all-reduce channel (peer stores over NVLink), so a dot product and its
+  // all-reduce are ONE kernel.  nullptr on a single GPU.
+  const ChanDev *ar = nullptr;
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -70,6 +142,31 @@ __device__ __forceinline__ double block_sum(double v, double *smem /*[32]*/) {
   }
   return v;
 }
+// in-place all-reduce (sum) of n <= kArCap block-local values over the ranks; called by ALL
+// threads of ONE block per rank.  Every rank stores its values into region [me] of every
+// rank's slot (itself included), releases its flag, acquires everybody's flag and adds the
+// regions in rank order: the result is bit-identical on every rank.
+__device__ __forceinline__ void ar_scalar(const ChanDev &ch, const double *s_vals, int n, double *out) {
+  __syncthreads();
+  const unsigned long long e = *ch.epoch + 1;
+  const size_t slot = (size_t)(e & 1ull);
+  for (int idx = threadIdx.x; idx < ch.nnb * n; idx += blockDim.x) {
+    const int k = idx / n, o = idx - k * n;
+    ch.nb_recv[k][slot * ch.nb_cap[k] + o] = s_vals[o];
+  }
+  __threadfence_system();
+  __syncthreads();
+  for (int k = threadIdx.x; k < ch.nnb; k += blockDim.x) st_release_sys(ch.nb_flag[k], e);
+  chan_wait(ch, e);
+  const double *base = ch.recv + slot * ch.cap;
+  for (int o = threadIdx.x; o < n; o += blockDim.x) {
+    double a = 0.0;
+    for (int r = 0; r < ch.nnb; ++r) a += base[(size_t)r * kArCap + o];
+    out[o] = a;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *ch.epoch = e;
+}
 // Every thread of every block must call this, once per slot and in slot order.
 // Deterministic: the final summation order depends only on gridDim.x and
 // blockDim.x.  Returns true (for all threads of the block) in the one block that
@@ -80,6 +177,7 @@ __device__ __forceinline__ bool reduce_finalize(double v, const Reducer &R, int 
   if (slot != n_out - 1) return false;
   // last slot of this block: publish all its partials and elect the last block
   __shared__ bool s_last;
+  __shared__ double s_res[kArCap];
   if (threadIdx.x == 0) {
     __threadfence();
     const unsigned int t = atomicInc(R.counter, gridDim.x - 1);
@@ -93,8 +191,14 @@ __device__ __forceinline__ bool reduce_finalize(double v, const Reducer &R, int 
       double a = 0.0;
       for (int b = threadIdx.x; b < gridDim.x; b += blockDim.x) a += R.partials[(size_t)b * n_out + o];
       a = block_sum(a, smem);
-      if (threadIdx.x == 0) R.out[o] = a;
+      if (threadIdx.x == 0) {
+        if (R.ar)
+          s_res[o] = a;
+        else
+          R.out[o] = a;
+      }
     }
+    if (R.ar) ar_scalar(*R.ar, s_res, n_out, R.out);
   }
   return last;
 }
@@ -282,56 +386,23 @@ __device__ __forceinline__ double row_partial(const CsrDev &A, const XVec &X, in
   return s;
 }
 
-// PF (opt-in, FDAL_SPMV_PF=1): the row pointers of the next grid-stride step and the epilogue's row
-// operands are fetched before the row is walked: rp -> (ci,v) -> x -> epilogue loads -> stores
-// becomes (ci,v) -> x -> stores.
-template <int TPR, class Epi, int U = 1, bool PF = false>
+template <int TPR, class Epi, int U = 1>
 __global__ void __launch_bounds__(kBlock) k_spmv(CsrDev A, XVec X, Epi epi, Reducer R) {
   __shared__ double smem[32];
   constexpr int rows_per_block = kBlock / TPR;
-  constexpr bool kPre = PF && EpiHasPrefetch<Epi>::value;
   const int lane = threadIdx.x & (TPR - 1);
   const int local_row = threadIdx.x / TPR;
   double contrib = 0.0;
-  int k0n = 0, k1n = 0;
-  if constexpr (PF) {
-    const long long row0 = (long long)blockIdx.x * rows_per_block + local_row;
-    if (row0 < A.nrows) {
-      k0n = __ldg(A.rp + row0);
-      k1n = __ldg(A.rp + row0 + 1);
-    }
-  }
-  for (long long base = (long long)blockIdx.x * rows_per_block; base < A.nrows;
-       base += (long long)gridDim.x * rows_per_block) {
-    const long long row = base + local_row;
+  HaloState hs;
+  halo_begin(X, hs);
+  const long long nchunks = ((long long)A.nrows + rows_per_block - 1) / rows_per_block;
+  for (long long p = blockIdx.x; p < nchunks; p += gridDim.x) {
+    const long long row = halo_chunk(X, hs, p) * rows_per_block + local_row;
     double s = 0.0;
-    [[maybe_unused]] typename PreOf<Epi, kPre>::type pre{};
-    if (row < A.nrows) {
-      int k0, k1;
-      if constexpr (PF) {
-        k0 = k0n;
-        k1 = k1n;
-        const long long rown = row + (long long)gridDim.x * rows_per_block;
-        if (rown < A.nrows) {
-          k0n = __ldg(A.rp + rown);
-          k1n = __ldg(A.rp + rown + 1);
-        }
-      } else {
-        k0 = __ldg(A.rp + row);
-        k1 = __ldg(A.rp + row + 1);
-      }
-      if constexpr (kPre)
-        if (lane == 0) pre = epi.prefetch((int)row);
-      s = row_partial<TPR, U>(A, X, k0, k1, lane);
-    }
+    if (row < A.nrows) s = row_partial<TPR, U>(A, X, __ldg(A.rp + row), __ldg(A.rp + row + 1), lane);
 #pragma unroll
     for (int o = TPR >> 1; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, TPR);
-    if (lane == 0 && row < A.nrows) {
-      if constexpr (kPre)
-        contrib += epi.finish((int)row, s, pre);
-      else
-        contrib += epi((int)row, s);
-    }
+    if (lane == 0 && row < A.nrows) contrib += epi((int)row, s);
   }
   if (Epi::kReduce) reduce_finalize(contrib, R, 0, 1, smem);
 }
@@ -340,63 +411,28 @@ __global__ void __launch_bounds__(kBlock) k_spmv(CsrDev A, XVec X, Epi epi, Redu
 // Two CSR matrices with the same row partition are walked in one row pass, so A x
 // never goes to memory before the coupling term is added (K3).  t already carries
 // gamma * W^-1 C x (phase 1), and for the block system also + x1.
-template <int TPR, class Epi, int U = 1, bool PF = false>
+template <int TPR, class Epi, int U = 1>
 __global__ void __launch_bounds__(kBlock) k_spmv2(CsrDev A, XVec X, CsrDev Ct, const double *__restrict__ t, Epi epi,
                                                    Reducer R) {
   __shared__ double smem[32];
   constexpr int rows_per_block = kBlock / TPR;
-  constexpr bool kPre = PF && EpiHasPrefetch<Epi>::value;
   const int lane = threadIdx.x & (TPR - 1);
   const int local_row = threadIdx.x / TPR;
   double contrib = 0.0;
-  int k0n = 0, k1n = 0, c0n = 0, c1n = 0;
-  if constexpr (PF) {
-    const long long row0 = (long long)blockIdx.x * rows_per_block + local_row;
-    if (row0 < A.nrows) {
-      k0n = __ldg(A.rp + row0);
-      k1n = __ldg(A.rp + row0 + 1);
-      c0n = __ldg(Ct.rp + row0);
-      c1n = __ldg(Ct.rp + row0 + 1);
-    }
-  }
-  for (long long base = (long long)blockIdx.x * rows_per_block; base < A.nrows;
-       base += (long long)gridDim.x * rows_per_block) {
-    const long long row = base + local_row;
+  HaloState hs;
+  halo_begin(X, hs);
+  const long long nchunks = ((long long)A.nrows + rows_per_block - 1) / rows_per_block;
+  for (long long p = blockIdx.x; p < nchunks; p += gridDim.x) {
+    const long long row = halo_chunk(X, hs, p) * rows_per_block + local_row;
     double s = 0.0;
-    [[maybe_unused]] typename PreOf<Epi, kPre>::type pre{};
     if (row < A.nrows) {
-      int k0, k1, c0, c1;
-      if constexpr (PF) {
-        k0 = k0n;
-        k1 = k1n;
-        c0 = c0n;
-        c1 = c1n;
-        const long long rown = row + (long long)gridDim.x * rows_per_block;
-        if (rown < A.nrows) {
-          k0n = __ldg(A.rp + rown);
-          k1n = __ldg(A.rp + rown + 1);
-          c0n = __ldg(Ct.rp + rown);
-          c1n = __ldg(Ct.rp + rown + 1);
-        }
-      } else {
-        k0 = __ldg(A.rp + row);
-        k1 = __ldg(A.rp + row + 1);
-        c0 = __ldg(Ct.rp + row);
-        c1 = __ldg(Ct.rp + row + 1);
-      }
-      if constexpr (kPre)
-        if (lane == 0) pre = epi.prefetch((int)row);
-      s = row_partial<TPR, U>(A, X, k0, k1, lane);
+      const int c0 = __ldg(Ct.rp + row), c1 = __ldg(Ct.rp + row + 1);
+      s = row_partial<TPR, U>(A, X, __ldg(A.rp + row), __ldg(A.rp + row + 1), lane);
       for (int k = c0 + lane; k < c1; k += TPR) s += __ldg(Ct.v + k) * __ldg(t + __ldg(Ct.ci + k));
     }
 #pragma unroll
     for (int o = TPR >> 1; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, TPR);
-    if (lane == 0 && row < A.nrows) {
-      if constexpr (kPre)
-        contrib += epi.finish((int)row, s, pre);
-      else
-        contrib += epi((int)row, s);
-    }
+    if (lane == 0 && row < A.nrows) contrib += epi((int)row, s);
   }
   if (Epi::kReduce) reduce_finalize(contrib, R, 0, 1, smem);
 }
@@ -418,7 +454,7 @@ struct BsrDev {
   int aos = 0;
 };
 
-template <int B, int TPR, class Epi, bool TWO, bool AOS, int U = 1>
+template <int B, int TPR, class Epi, bool TWO, int U = 1>
 __global__ void __launch_bounds__(kBlock) k_bsr_spmv(BsrDev A, XVec X, CsrDev C2, const double *__restrict__ t2, Epi epi,
                                                       Reducer R) {
   __shared__ double smem[32];
@@ -429,17 +465,22 @@ __global__ void __launch_bounds__(kBlock) k_bsr_spmv(BsrDev A, XVec X, CsrDev C2
   double contrib = 0.0;
   // U >= 4 (opt-in variant): the block-row pointers of the NEXT grid-stride step are fetched while
   // this step's blocks are in flight, which takes one DRAM latency out of every step's chain
+  HaloState hs;
+  halo_begin(X, hs);
+  const long long nchunks = ((long long)A.nbrows + rows_per_block - 1) / rows_per_block;
+  auto chunk_of = [&](long long p) { return X.order ? (long long)__ldg(X.order + p) : p; };
   int k0n = 0, k1n = 0;
   if constexpr (U >= 4) {
-    const long long I0 = (long long)blockIdx.x * rows_per_block + local_row;
-    if (I0 < A.nbrows) {
-      k0n = __ldg(A.rp + I0);
-      k1n = __ldg(A.rp + I0 + 1);
+    if ((long long)blockIdx.x < nchunks) {
+      const long long I0 = chunk_of(blockIdx.x) * rows_per_block + local_row;
+      if (I0 < A.nbrows) {
+        k0n = __ldg(A.rp + I0);
+        k1n = __ldg(A.rp + I0 + 1);
+      }
     }
   }
-  for (long long base = (long long)blockIdx.x * rows_per_block; base < A.nbrows;
-       base += (long long)gridDim.x * rows_per_block) {
-    const long long I = base + local_row;
+  for (long long p = blockIdx.x; p < nchunks; p += gridDim.x) {
+    const long long I = halo_chunk(X, hs, p) * rows_per_block + local_row;
     double s[B];
 #pragma unroll
     for (int r = 0; r < B; ++r) s[r] = 0.0;
@@ -449,10 +490,13 @@ __global__ void __launch_bounds__(kBlock) k_bsr_spmv(BsrDev A, XVec X, CsrDev C2
       if constexpr (U >= 4) {
         k0 = k0n;
         k1 = k1n;
-        const long long In = I + (long long)gridDim.x * rows_per_block;
-        if (In < A.nbrows) {
-          k0n = __ldg(A.rp + In);
-          k1n = __ldg(A.rp + In + 1);
+        const long long pn = p + gridDim.x;
+        if (pn < nchunks) {
+          const long long In = chunk_of(pn) * rows_per_block + local_row;
+          if (In < A.nbrows) {
+            k0n = __ldg(A.rp + In);
+            k1n = __ldg(A.rp + In + 1);
+          }
         }
       } else {
         k0 = __ldg(A.rp + I);
@@ -470,12 +514,13 @@ __global__ void __launch_bounds__(kBlock) k_bsr_spmv(BsrDev A, XVec X, CsrDev C2
           const int k = kk + u * TPR;
           const bool ok = k < nb;
           const int c = (ok ? __ldg(A.cj + k0 + k) : 0) * B;
-          const double *xp = c < X.n_owned ? X.x + c : X.halo + (c - X.n_owned);
+          const bool own = c < X.n_owned;
+          const double *xp = own ? X.x + c : X.halo + (c - X.n_owned);
 #pragma unroll
           for (int q = 0; q < B * B; ++q)
-            a[u][q] = ok ? (AOS ? __ldg(vb + (size_t)k * (B * B) + q) : __ldg(vb + (size_t)q * nb + k)) : 0.0;
+            a[u][q] = ok ? __ldg(vb + (size_t)k * (B * B) + q) : 0.0;
 #pragma unroll
-          for (int q = 0; q < B; ++q) xj[u][q] = ok ? __ldg(xp + q) : 0.0;
+          for (int q = 0; q < B; ++q) xj[u][q] = ok ? (own ? __ldg(xp + q) : xp[q]) : 0.0;
         }
 #pragma unroll
         for (int u = 0; u < U; ++u)
@@ -511,130 +556,6 @@ __global__ void __launch_bounds__(kBlock) k_bsr_spmv(BsrDev A, XVec X, CsrDev C2
     }
   }
   if (Epi::kReduce) reduce_finalize(contrib, R, 0, 1, smem);
-}
-
-// ---- TMA-staged CSR SpMV ("stream" variant, the default) ---------------------------
-// The value / column arrays of a run of whole rows (a "chunk", <= kChunk non-zeros,
-// row-aligned, built once at upload) are one contiguous byte range each, so a single
-// elected thread moves them global -> shared with two 1-D bulk copies
-// (cp.async.bulk, SASS UBLKCP) that complete on an mbarrier.  CTAs are persistent and
-// double-buffered: while chunk i is processed, chunk i+1 is already in flight, so
-// the HBM stream never waits for the latency-bound x gathers.  Phase A: every
-// thread multiplies kChunk/kBlock staged non-zeros with gathered x (independent
-// gathers, mostly L2 hits) and parks the products in shared memory.  Phase B: TPR
-// lanes per row reduce the row's products from shared memory (conflict-free) and run
-// the fused epilogue.  With TWO a second CSR matrix with the same rows (Ct, a handful
-// of non-zeros) is added from global memory in phase B: y = A x + Ct t in one pass.
-constexpr int kChunk = 2048;
-constexpr int kChunkCap = kChunk + 8;
-constexpr int kStreamSmemBytes = 2 * kChunkCap * 8 + 2 * kChunkCap * 4 + kChunkCap * 8 + 32;
-
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-
-struct StreamPlan {
-  const int4 *desc;  // [nblk] {first row, end row, first element (4-aligned), element count (4-aligned)}
-  int nblk;
-};
-
-template <int TPR, class Epi, bool TWO>
-__global__ void __launch_bounds__(kBlock) k_spmv_stream(CsrDev A, StreamPlan plan, XVec X, CsrDev B2,
-                                                         const double *__restrict__ t2, Epi epi, Reducer R) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  double *sv = reinterpret_cast<double *>(smem_raw);                     // [2][kChunkCap]
-  double *sprod = sv + 2 * kChunkCap;                                    // [kChunkCap]
-  int *sci = reinterpret_cast<int *>(sprod + kChunkCap);                 // [2][kChunkCap]
-  unsigned long long *bar = reinterpret_cast<unsigned long long *>(sci + 2 * kChunkCap);  // [2]
-  __shared__ double red_smem[32];
-
-  const int tid = threadIdx.x;
-  if (tid == 0) {
-    mbar_init(&bar[0], 1);
-    mbar_init(&bar[1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-
-  auto issue = [&](int blk, int stage) {
-    const int4 dsc = __ldg(plan.desc + blk);
-    const int e0 = dsc.z;
-    const unsigned n = (unsigned)dsc.w;
-    if (n) {
-      mbar_expect_tx(&bar[stage], n * 12u);
-      bulk_g2s(sv + stage * kChunkCap, A.v + e0, n * 8u, &bar[stage]);
-      bulk_g2s(sci + stage * kChunkCap, A.ci + e0, n * 4u, &bar[stage]);
-    }
-  };
-
-  unsigned parity[2] = {0u, 0u};
-  int stage = 0;
-  double contrib = 0.0;
-  if (tid == 0 && (int)blockIdx.x < plan.nblk) issue(blockIdx.x, 0);
-
-  constexpr int groups = kBlock / TPR;
-  const int lane = tid & (TPR - 1);
-  const int group = tid / TPR;
-
-  for (int blk = blockIdx.x; blk < plan.nblk; blk += gridDim.x) {
-    const int nxt = blk + gridDim.x;
-    if (tid == 0 && nxt < plan.nblk) issue(nxt, stage ^ 1);
-    const int4 dsc = __ldg(plan.desc + blk);
-    const int r0 = dsc.x, r1 = dsc.y, e0 = dsc.z, n = dsc.w;
-    if (n) {
-      mbar_wait(&bar[stage], parity[stage]);
-      parity[stage] ^= 1u;
-    }
-    // phase A: products of the staged non-zeros with gathered x
-    const double *cv = sv + stage * kChunkCap;
-    const int *cc = sci + stage * kChunkCap;
-#pragma unroll 4
-    for (int j = tid; j < n; j += kBlock) sprod[j] = cv[j] * xload(X, cc[j]);
-    __syncthreads();
-    // phase B: per-row reduction + fused epilogue
-    const int nrows = r1 - r0;
-    for (int base = 0; base < nrows; base += groups) {
-      const int row = r0 + base + group;
-      double s = 0.0;
-      if (row < r1) {
-        const int k0 = __ldg(A.rp + row) - e0, k1 = __ldg(A.rp + row + 1) - e0;
-        for (int k = k0 + lane; k < k1; k += TPR) s += sprod[k];
-        if (TWO) {
-          const int c0 = __ldg(B2.rp + row), c1 = __ldg(B2.rp + row + 1);
-          for (int k = c0 + lane; k < c1; k += TPR) s += __ldg(B2.v + k) * __ldg(t2 + __ldg(B2.ci + k));
-        }
-      }
-#pragma unroll
-      for (int o = TPR >> 1; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, TPR);
-      if (lane == 0 && row < r1) contrib += epi(row, s);
-    }
-    __syncthreads();  // sprod and this stage's buffers are free again
-    stage ^= 1;
-  }
-  if (Epi::kReduce) reduce_finalize(contrib, R, 0, 1, red_smem);
 }
 
 // ---- dense GEMV for the coarsest AMG level: y = Ainv b (one warp per row) --------
@@ -677,6 +598,66 @@ __global__ void k_dense_square(int n, const double *__restrict__ A, double *__re
   double s = 0.0;
   for (int k = 0; k < n; ++k) s += row[k] * A[(size_t)k * n + c];
   C[(size_t)r * n + c] = s;
+}
+// ---- exchange-channel kernels (multi-GPU, peers mapped through cudaIpc) ------------------
+// elect the last block of a push kernel; it releases the new epoch to every neighbour
+__device__ __forceinline__ void chan_publish(const ChanDev &ch, unsigned long long e) {
+  __shared__ bool s_last_push;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int nblk = gridDim.x * gridDim.y;
+    s_last_push = atomicInc(ch.counter, nblk - 1) == nblk - 1;
+  }
+  __syncthreads();
+  if (s_last_push) {
+    __threadfence_system();
+    for (int k = threadIdx.x; k < ch.nnb; k += blockDim.x) st_release_sys(ch.nb_flag[k], e);
+    if (threadIdx.x == 0) *ch.epoch = e;
+  }
+}
+// halo push: entry i of my send list (grouped by neighbour) goes straight into that neighbour's
+// receive slot — the "pack" and the transfer are the same NVLink stores
+__global__ void __launch_bounds__(kBlock) k_chan_push_gather(ChanDev ch, const int *__restrict__ idx,
+                                                              const double *__restrict__ x) {
+  const unsigned long long e = *ch.epoch + 1;
+  chan_wait(ch, e - 1);  // every neighbour has finished reading slot (e & 1) of epoch e - 2
+  const size_t slot = (size_t)(e & 1ull);
+  const int n = ch.nb_begin[ch.nnb];
+  for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+    int k = 0;
+    while (i >= ch.nb_begin[k + 1]) ++k;
+    ch.nb_recv[k][slot * ch.nb_cap[k] + (i - ch.nb_begin[k])] = x[idx[i]];
+  }
+  chan_publish(ch, e);
+}
+// broadcast push (all-gather / vector all-reduce): x[0:n) into my region of every rank (blockIdx.y)
+__global__ void __launch_bounds__(kBlock) k_chan_push_bcast(ChanDev ch, const double *__restrict__ x, int n) {
+  const unsigned long long e = *ch.epoch + 1;
+  chan_wait(ch, e - 1);
+  const size_t slot = (size_t)(e & 1ull);
+  const int k = blockIdx.y;
+  double *dst = ch.nb_recv[k] + slot * ch.nb_cap[k];
+  for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) dst[i] = x[i];
+  chan_publish(ch, e);
+}
+// consumer of a broadcast channel.  SUM: out[i] = sum over ranks (in rank order: bit-identical on
+// all ranks) of region r; else the regions tile the slot (all-gather) and out = the slot.
+// scale_in/add fuse the epilogue of the coupling phase 1 (see k_couple_elem).
+template <bool SUM>
+__global__ void __launch_bounds__(kBlock) k_chan_collect(ChanDev ch, double *__restrict__ out, int n, int stride) {
+  const unsigned long long e = *ch.epoch;
+  chan_wait(ch, e);
+  const double *base = ch.recv + (size_t)(e & 1ull) * ch.cap;
+  for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+    if (SUM) {
+      double a = 0.0;
+      for (int r = 0; r < ch.nnb; ++r) a += base[(size_t)r * stride + i];
+      out[i] = a;
+    } else {
+      out[i] = base[i];
+    }
+  }
 }
 // halo pack: buf[i] = x[idx[i]]
 __global__ void __launch_bounds__(kBlock) k_pack(int n, const int *__restrict__ idx, const double *__restrict__ x,

@@ -177,12 +177,28 @@ class LocalLevel:
 
 @dataclass
 class LocalHierarchy:
-    levels: list
-    coarse_A: sp.csr_matrix  # replicated (renumbered) coarsest operator
-    coarse_off: np.ndarray
+    levels: list  # levels[:rep_from] row-partitioned, levels[rep_from:] replicated (all but the coarsest)
+    coarse_A: sp.csr_matrix  # replicated coarsest operator
+    coarse_off: np.ndarray  # ownership of the rows of level rep_from (all-gather of the restricted residual)
     cheb_degree: int
     eig_ratio: float
+    rep_from: int = -1  # first replicated level (-1: only the coarsest operator)
     replicated: bool = False
+
+
+def replicate_from(sizes, nranks: int, max_rows: int | None = None) -> int:
+    """First level of the hierarchy that is agglomerated onto every rank: the first one (after the
+    finest) with at most ``max_rows`` rows (env FDAL_REP_ROWS, default 60000); the coarsest level is
+    always replicated.  Below that size a halo exchange costs more than the rows it saves."""
+    import os
+
+    if max_rows is None:
+        max_rows = int(os.environ.get("FDAL_REP_ROWS", "60000"))
+    nl = len(sizes)
+    for l in range(1, nl):
+        if sizes[l] <= max_rows:
+            return l
+    return nl - 1
 
 
 @dataclass
@@ -283,21 +299,29 @@ class Distributor:
             if which != b.AMG_A11:
                 self.hier[which] = H  # immersed block: replicated
                 continue
+            nl = len(H.levels)
+            rep_from = replicate_from([L.A.shape[0] for L in H.levels], nranks) if nranks > 1 else nl - 1
             levels = []
             order_f, off_f = self.order0, self.off0
+            rep_off = off_f
             Aperm = _perm(H.levels[0].A, order_f, order_f)
-            for l in range(len(H.levels) - 1):
+            for l in range(nl - 1):
                 L = H.levels[l]
-                order_c, off_c = coarse_order(_perm(L.P, order_f, None), off_f)
+                if l < rep_from:
+                    order_c, off_c = coarse_order(_perm(L.P, order_f, None), off_f)
+                else:
+                    order_c, off_c = None, None  # replicated levels keep the hierarchy's own numbering
                 Pp = _perm(L.P, order_f, order_c)
                 Rp = _perm(L.R if L.R is not None else L.P.T, order_c, order_f)
                 invd = None if L.inv_diag is None else (L.inv_diag if order_f is None else L.inv_diag[order_f])
                 levels.append(dict(A=Aperm, P=Pp, R=Rp, inv_diag=invd, lambda_max=L.lambda_max, off_f=off_f, off_c=off_c,
-                                   bs=self.bs if l == 0 else 1))
+                                   bs=self.bs if l == 0 else 1, part=l < rep_from, last_part=l == rep_from - 1))
+                if l == rep_from - 1:
+                    rep_off = off_c
                 order_f, off_f = order_c, off_c
                 Aperm = _perm(H.levels[l + 1].A, order_f, order_f)
-            self.hier[which] = dict(levels=levels, coarse_A=Aperm, coarse_off=off_f, cheb_degree=H.cheb_degree,
-                                    eig_ratio=H.eig_ratio)
+            self.hier[which] = dict(levels=levels, coarse_A=Aperm, coarse_off=rep_off, cheb_degree=H.cheb_degree,
+                                    eig_ratio=H.eig_ratio, rep_from=rep_from)
 
     def local(self, rank: int) -> LocalProblem:
         prob, nranks, off0, bs = self.prob, self.nranks, self.off0, self.bs
@@ -331,14 +355,25 @@ class Distributor:
             levels = []
             for L in Hd["levels"]:
                 off_f, off_c = L["off_f"], L["off_c"]
+                if not L["part"]:  # agglomerated level: the whole matrices on every rank, no exchange
+                    levels.append(LocalLevel(A=DistCsr(L["A"], None), P=DistCsr(L["P"], None), R=DistCsr(L["R"], None),
+                                             inv_diag=L["inv_diag"], lambda_max=L["lambda_max"]))
+                    continue
+                if L["last_part"] and nranks > 1:
+                    # the next level is replicated: P reads the full coarse vector (global columns, no
+                    # halo), R produces this rank's rows of it (all-gathered afterwards)
+                    P_loc = DistCsr(L["P"][int(off_f[rank]): int(off_f[rank + 1])].tocsr(), None)
+                else:
+                    P_loc = localize(L["P"], off_f, off_c, rank)
                 levels.append(LocalLevel(
                     A=localize(L["A"], off_f, off_f, rank, L["bs"]),
-                    P=localize(L["P"], off_f, off_c, rank),
+                    P=P_loc,
                     R=localize(L["R"], off_c, off_f, rank, L["bs"]),
                     inv_diag=None if L["inv_diag"] is None else L["inv_diag"][off_f[rank]: off_f[rank + 1]],
                     lambda_max=L["lambda_max"]))
             lp.amg[which] = LocalHierarchy(levels=levels, coarse_A=Hd["coarse_A"], coarse_off=Hd["coarse_off"],
-                                           cheb_degree=Hd["cheb_degree"], eig_ratio=Hd["eig_ratio"])
+                                           cheb_degree=Hd["cheb_degree"], eig_ratio=Hd["eig_ratio"],
+                                           rep_from=Hd["rep_from"])
         return lp
 
 

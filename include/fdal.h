@@ -292,8 +292,19 @@ int fdal_comm_init(fdal_ctx *ctx, const char id[128], int rank, int n_ranks);
 int fdal_set_halo(fdal_ctx *ctx, int matrix_id, int level, int which,
                   int64_t n_owned_cols, int64_t n_halo, const int32_t *send_counts,
                   const int32_t *send_idx, const int32_t *recv_counts);
-/* rows [lo, hi) of the replicated coarsest operator belong to this rank */
+/* Agglomeration: levels >= `level` of hierarchy `which` are replicated on every rank (full
+ * matrices, no halo plans; default: only the coarsest operator).  The last partitioned level's P
+ * then has GLOBAL columns of level `level` and its R has this rank's rows [lo, hi) of that level
+ * (fdal_amg_set_coarse_range); the restricted residual is all-gathered, everything below runs
+ * redundantly without communication. */
+int fdal_amg_set_replicated_from(fdal_ctx *ctx, int which, int level);
+/* rows [lo, hi) of the first replicated level belong to this rank */
 int fdal_amg_set_coarse_range(fdal_ctx *ctx, int which, int64_t lo, int64_t hi);
+/* 0: single rank; 1: NCCL send/recv + all-reduce per exchange (fallback, FDAL_COMM=nccl);
+ * 2: peer channels — every rank maps the others' exchange arena (cudaIpc) and halos, scalar and
+ * vector all-reduces and the coarse all-gather are NVLink stores + flags issued by this
+ * library's own kernels (fused into the reductions' last block / the SpMV's boundary chunks) */
+int fdal_comm_mode(const fdal_ctx *ctx);
 
 #ifdef __cplusplus
 }

@@ -1,5 +1,7 @@
-"""Row-partitioned solve on 2 GPUs (NCCL halo exchange + all-reduce) against the serial
-CPU oracle.  Needs >= 2 CUDA devices: skipped otherwise (run with `gpurun --gpus 2`)."""
+"""Row-partitioned solve on 2 (and 4) GPUs against the serial CPU oracle, in both communication
+modes: peer channels (cudaIpc-mapped halo / all-reduce / all-gather buffers written by the library's
+own kernels, the default) and the NCCL send/recv + all-reduce fallback.  Needs >= 2 CUDA devices:
+skipped otherwise (run with `gpurun --gpus 2`)."""
 import os
 import socket
 
@@ -20,9 +22,18 @@ def _free_port():
     return p
 
 
-def _worker(rank, nranks, port, case, q):
+def _worker(rank, nranks, port, case, mode, q):
+    import threading
+
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
+    os.environ["FDAL_COMM"] = "nccl" if mode == "nccl" else "p2p"
+    if mode == "p2p_deep":  # partition every AMG level but the coarsest
+        os.environ["FDAL_REP_ROWS"] = "0"
+    # a rank stuck in a spinning kernel would otherwise outlive the test
+    wd = threading.Timer(180, lambda: os._exit(7))
+    wd.daemon = True
+    wd.start()
     dist.init_process_group("gloo", rank=rank, world_size=nranks)
     try:
         from fictitious_domain_al_preconditioners_b200 import ALContext
@@ -39,7 +50,7 @@ def _worker(rank, nranks, port, case, q):
         uid = [ctx.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         part.setup_local_context(ctx, lp, uid[0])
-        res = {}
+        res = {"comm_mode": ctx.api.comm_mode(ctx._h), "rep_from": lp.amg[0].rep_from, "levels": len(lp.amg[0].levels)}
         # operator / preconditioner applications on scattered random vectors
         X = P.rand(prob.n_dofs, 5)
         y_loc = ctx.apply_system(lp.scatter(X))
@@ -82,21 +93,37 @@ def _worker(rank, nranks, port, case, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("case", ["laplace_diag", "stokes2d_diag", "stokes3d_diag", "stokes2d_exact", "elliptic_modified_diag"])
-def test_two_gpu_solve_matches_oracle(case):
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+CASES = [("laplace_diag", 2, "p2p"), ("stokes2d_diag", 2, "p2p"), ("stokes3d_diag", 2, "p2p"),
+         ("stokes2d_exact", 2, "p2p"), ("elliptic_modified_diag", 2, "p2p"), ("elliptic_ideal", 2, "p2p"),
+         ("stokes2d_diag", 2, "p2p_deep"), ("stokes3d_diag", 2, "p2p_deep"),
+         ("stokes2d_diag", 2, "nccl"), ("stokes3d_diag", 2, "nccl"),
+         ("stokes3d_diag", 4, "p2p"), ("stokes2d_diag", 4, "p2p_deep"), ("laplace_diag", 4, "p2p")]
+
+
+@pytest.mark.parametrize("case,nranks,mode", CASES)
+def test_multi_gpu_solve_matches_oracle(case, nranks, mode):
+    if torch.cuda.device_count() < nranks:
+        pytest.skip(f"needs {nranks} GPUs")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, case, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, nranks, port, case, mode, q)) for r in range(nranks)]
     for p in procs:
         p.start()
-    res = q.get(timeout=600)
+    try:
+        res = q.get(timeout=200)
+    finally:
+        for p in procs:
+            p.join(timeout=30)
+            if p.is_alive():
+                p.kill()
     for p in procs:
-        p.join(timeout=120)
         assert p.exitcode == 0
-    print(case, res)
+    print(case, nranks, mode, res)
+    from tests import parity_log
+
+    parity_log.record(f"multi_gpu[{case},{nranks},{mode}]", res)
+    assert res["comm_mode"] == (1 if mode == "nccl" else 2)
     assert res["system"] < 1e-12
     assert res["amg"] < 1e-12
     assert res["rhs"] < 1e-12
@@ -104,4 +131,7 @@ def test_two_gpu_solve_matches_oracle(case):
     assert res["prec"] < 1e-9
     assert abs(res["outer"][0] - res["outer"][1]) <= 1
     if res["outer"][0] == res["outer"][1]:
-        assert res["solve"] < 1e-8
+        # identical inner trajectories reproduce the solution to solver accuracy; where one inner CG stopped an
+        # iteration apart (block-CG of the ideal variant: see the self-sensitivity note in test_gpu_parity.py) the
+        # two runs are different, equally valid, approximate preconditioners
+        assert res["solve"] < (1e-8 if res["inner"][0] == res["inner"][1] else 1e-5)

@@ -52,14 +52,16 @@ def allreduce(v):
 
 
 def dist_vcycle(LH, bvec, rank, nranks, l=0):
-    """Distributed restatement of the V-cycle on LocalHierarchy pieces."""
-    if l == len(LH.levels):
-        off = LH.coarse_off
-        full = np.zeros(LH.coarse_A.shape[0])
-        full[off[rank]: off[rank + 1]] = bvec
-        full = allreduce(full)
-        return np.linalg.solve(LH.coarse_A.toarray(), full)[off[rank]: off[rank + 1]]
+    """Distributed restatement of the V-cycle on LocalHierarchy pieces: levels
+    below LH.rep_from are row-partitioned (halo exchanges), the restricted residual of the last
+    partitioned level is all-gathered, the levels from rep_from on run replicated."""
+    nl = len(LH.levels)
+    rep_from = LH.rep_from if LH.rep_from >= 0 else nl
+    if l == nl:
+        return np.linalg.solve(LH.coarse_A.toarray(), bvec)  # replicated: bvec is the full vector
     L = LH.levels[l]
+    if l >= rep_from:
+        assert L.A.plan is None and L.P.plan is None and L.R.plan is None
     invd = L.inv_diag
     beta, alpha = 1.1 * L.lambda_max, L.lambda_max / LH.eig_ratio
     delta, theta = 0.5 * (beta - alpha), 0.5 * (beta + alpha)
@@ -79,7 +81,15 @@ def dist_vcycle(LH, bvec, rank, nranks, l=0):
 
     x = cheb(None, True)
     r = bvec - mv(x)
-    e = dist_vcycle(LH, dist_spmv(L.R, r, rank, nranks), rank, nranks, l + 1)
+    rc = dist_spmv(L.R, r, rank, nranks)
+    if l == rep_from - 1 and nranks > 1:
+        off = LH.coarse_off
+        assert rc.size == off[rank + 1] - off[rank]
+        full = np.zeros(int(off[-1]))
+        full[off[rank]: off[rank + 1]] = rc
+        rc = allreduce(full)  # all-gather of the owned rows
+        assert L.P.plan is None  # reads the replicated coarse vector through global columns
+    e = dist_vcycle(LH, rc, rank, nranks, l + 1)
     x = x + dist_spmv(L.P, e, rank, nranks)
     return cheb(x, False)
 
@@ -89,6 +99,9 @@ def _ord(v, order):
 
 
 def _worker(rank, nranks, port, case, q):
+    if case.endswith("@deep"):  # partition every level but the coarsest (no agglomeration)
+        os.environ["FDAL_REP_ROWS"] = "0"
+        case = case[:-5]
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=nranks)
@@ -154,10 +167,12 @@ def _worker_body(rank, nranks, case, q):
         zref = _ord(vcycle_ref(H[b.AMG_A11], X[:n]), lp.order0)[lp.off0[rank]: lp.off0[rank + 1]]
         res["vcycle"] = float(np.abs(z - zref).max() / np.abs(zref).max())
         res["levels"] = len(LH.levels)
+        res["rep_from"] = LH.rep_from
         q.put((rank, res))
 
 
-@pytest.mark.parametrize("case,nranks", [("laplace", 2), ("stokes", 2), ("stokes_node", 2), ("stokes3d_node", 4)])
+@pytest.mark.parametrize("case,nranks", [("laplace", 2), ("stokes", 2), ("stokes_node", 2), ("stokes3d_node", 4),
+                                         ("laplace@deep", 2), ("stokes_node@deep", 2), ("stokes3d_node@deep", 4)])
 def test_partition_matches_serial(case, nranks):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -171,7 +186,11 @@ def test_partition_matches_serial(case, nranks):
         assert p.exitcode == 0
     for rank, res in out:
         assert "error" not in res, res.get("error")
-        assert res.pop("levels") >= 1
+        nlev = res.pop("levels")
+        rep = res.pop("rep_from")
+        assert nlev >= 1 and 1 <= rep <= nlev
+        if case.endswith("@deep"):
+            assert rep == nlev
         for k, v in res.items():
             assert v < 1e-11, (rank, k, v)
 
