@@ -30,3 +30,10 @@ def record(test: str, values: dict):
             f.write(json.dumps({"test": test, **_plain(values)}) + "\n")
     except Exception:
         pass
+
+
+def check(what: str, err: float, tol: float, **extra):
+    """Assert err < tol and log both (the test id comes from pytest's PYTEST_CURRENT_TEST)."""
+    test = os.environ.get("PYTEST_CURRENT_TEST", "?").split(" ")[0].split("::", 1)[-1]
+    record(test, {"what": what, "err": float(err), "tol": float(tol), **extra})
+    assert err < tol, (what, err, tol)

@@ -17,9 +17,7 @@ def _make(kind, oracle_mod, cfg):
     return oracle_mod.OracleContext(cfg) if kind == "oracle" else ALContext(cfg)
 
 
-# the CUDA leg was written after the last GPU run of round 1: non-strict xfail until it has been seen green once
-KINDS = ["oracle", pytest.param("cuda", marks=[pytest.mark.gpu, pytest.mark.xfail(
-    strict=False, reason="CUDA leg not yet run on a GPU (written after the last GPU call of round 1)")])]
+KINDS = ["oracle", pytest.param("cuda", marks=[pytest.mark.gpu])]
 
 
 def _raw_set_csr(ctx, mid, nr, nc, rp, ci, v):
@@ -105,3 +103,80 @@ def test_empty_and_ragged_rows(kind, oracle_mod):
     g = prob.config.gamma
     ref = prob.A @ x + g * (Ct @ (prob.winv_diag * (Ct.T @ x)))
     assert P.relerr(ctx.apply_aug(x), ref) < 1e-12
+
+
+# ---- CUDA library only: state and hierarchy validation -------------------------------
+@pytest.mark.gpu
+def test_setters_after_finalize_are_refused():
+    """A finalized context owns device copies and captured graphs: every setter now returns
+    FDAL_ERR_STATE (instead of silently un-finalizing a context that can never be finalized again);
+    the solve entry points keep working."""
+    prob, H = P.get("laplace_diag")
+    ctx = syn.setup_context(ALContext(prob.config), prob, H)
+    x0, _ = ctx.solve(P.rhs_of(ctx, prob))
+    for call in (lambda: ctx.set_csr(b.MAT_CT, prob.Ct), lambda: ctx.set_diag(b.DIAG_W_INV, prob.winv_diag),
+                 lambda: ctx.set_amg(b.AMG_A11, H[b.AMG_A11])):
+        with pytest.raises(FdalError) as e:
+            call()
+        assert e.value.status == b.ERR_STATE and "finalized" in str(e.value)
+    x1, info = ctx.solve(P.rhs_of(ctx, prob))
+    assert info.status == 0 and np.array_equal(x0, x1)
+
+
+def _view(A):
+    return b.csr_view(sp.csr_matrix(A))
+
+
+@pytest.mark.gpu
+def test_malformed_hierarchy_is_rejected():
+    """fdal_amg_set_level validates its CSR views like fdal_set_csr; fdal_finalize checks the shapes
+    between levels and the Chebyshev parameters before anything is launched."""
+    prob, H = P.get("laplace_diag")
+    L0, L1 = H[b.AMG_A11].levels[0], H[b.AMG_A11].levels[1]
+
+    def fresh():
+        c = ALContext(prob.config)
+        c.set_csr(b.MAT_A, prob.A)
+        c.set_csr(b.MAT_CT, prob.Ct)
+        c.set_csr(b.MAT_M, prob.M)
+        c.set_diag(b.DIAG_W_INV, prob.winv_diag)
+        return c
+
+    def set_level(c, level, A, Pm, R, degree=2, lmax=1.5, ratio=10.0):
+        Av, ka = _view(A)
+        Pv, kp = _view(Pm) if Pm is not None else (None, None)
+        Rv, kr = _view(R) if R is not None else (None, None)
+        return c.api.amg_set_level(c._h, b.AMG_A11, level, C.byref(Av), C.byref(Pv) if Pv is not None else None,
+                                   C.byref(Rv) if Rv is not None else None, None, lmax, degree, ratio)
+
+    # a view with a column index out of range never reaches the device
+    c = fresh()
+    bad = sp.csr_matrix(L0.P).copy()
+    bad.indices = bad.indices.copy()
+    bad.indices[0] = bad.shape[1] + 7
+    Av, ka = _view(L0.A)
+    rp, ci, v = b.csr_arrays(bad)
+    Pv = b.CsrView(bad.shape[0], bad.shape[1], v.size, rp.ctypes.data_as(C.POINTER(C.c_int64)),
+                   ci.ctypes.data_as(C.POINTER(C.c_int32)), v.ctypes.data_as(C.POINTER(C.c_double)))
+    assert c.api.amg_set_level(c._h, b.AMG_A11, 0, C.byref(Av), C.byref(Pv), None, None, 1.5, 2, 10.0) == b.ERR_SHAPE
+    # Chebyshev degree 0 on a smoothed level (the V-cycle would never write its result)
+    c = fresh()
+    assert set_level(c, 0, L0.A, L0.P, L0.R, degree=0) == b.OK
+    assert set_level(c, 1, L1.A, None, None) == b.OK
+    with pytest.raises(FdalError) as e:
+        c.finalize()
+    assert e.value.status == b.ERR_INVALID
+    # R with the wrong shape
+    c = fresh()
+    assert set_level(c, 0, L0.A, L0.P, sp.csr_matrix(L0.R)[:-1]) == b.OK
+    assert set_level(c, 1, L1.A, None, None) == b.OK
+    with pytest.raises(FdalError) as e:
+        c.finalize()
+    assert e.value.status == b.ERR_SHAPE
+    # P whose column count is not the next level's row count
+    c = fresh()
+    assert set_level(c, 0, L0.A, sp.csr_matrix(L0.P)[:, :-1], None) == b.OK
+    assert set_level(c, 1, L1.A, None, None) == b.OK
+    with pytest.raises(FdalError) as e:
+        c.finalize()
+    assert e.value.status == b.ERR_SHAPE

@@ -15,9 +15,7 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("kw", [
-    # the 3-D case ran green on a B200; the 1 M-DoF case was written after the last GPU call of round 1
-    pytest.param(dict(dim=2, nel=320, diagonal_mass=False), id="stokes2d_1M_as_shipped",
-                 marks=pytest.mark.xfail(strict=False, reason="not yet run on a GPU")),
+    pytest.param(dict(dim=2, nel=320, diagonal_mass=False), id="stokes2d_1M_as_shipped"),
     pytest.param(dict(dim=3, nel=16), id="stokes3d_nel16")])
 def test_properties_at_full_size(kw):
     prob = syn.stokes_immersed_boundary(numbering="node", **kw)

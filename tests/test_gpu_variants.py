@@ -1,7 +1,11 @@
-"""CUDA paths that exist but were not run on a GPU before the round ended.  Non-strict xfail and
-collected LAST (file name), so whatever they do cannot disturb the verified suites."""
+"""Further CUDA paths against the oracle and against the reference-derived golden vectors: the extra
+problem variants (no-grad-div Stokes, nitsche_bcs), the golden vectors of the reference's own
+preconditioner header through the C ABI, both exact-W^-1 paths (dense GEMV / single-CTA PCG), both
+BSR kernel variants, and the reference's classes bound to the CUDA library.  All ordinary (strict)
+tests: they ran green on a B200 in round 1's driver run (then still marked xfail) and in round 2."""
 import pytest
 
+from . import parity_log as PL
 from . import problems as P
 from .golden.generate_ref_prec import REF_CASES
 from .test_gpu_parity import _pair
@@ -9,27 +13,25 @@ from .test_gpu_parity import _pair
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.xfail(strict=False, reason="CUDA path of the no-grad-div Stokes variant was not run on a GPU in round 1")
 @pytest.mark.parametrize("name", list(P.EXTRA_CASES))
-def test_extra_cases_not_yet_run_on_gpu(name, oracle_mod):
+def test_extra_cases(name, oracle_mod):
     prob, gpu, ora = _pair(name, oracle_mod)
     x = P.rand(prob.sizes[0], 3)
-    assert P.relerr(gpu.apply_aug(x), ora.apply_aug(x)) < 1e-10
+    PL.check("apply_aug", P.relerr(gpu.apply_aug(x), ora.apply_aug(x)), 1e-10)
     X = P.rand(prob.n_dofs, 5)
-    assert P.relerr(gpu.apply_system(X), ora.apply_system(X)) < 1e-10
+    PL.check("apply_system", P.relerr(gpu.apply_system(X), ora.apply_system(X)), 1e-10)
     rhs = P.rhs_of(ora, prob)
     xg, ig = gpu.solve(rhs)
     xo, io = ora.solve(rhs)
     assert abs(ig.outer_iterations - io.outer_iterations) <= 1
     if ig.outer_iterations == io.outer_iterations:
-        assert P.relerr(xg, xo) < 1e-8
+        PL.check("solve: solution", P.relerr(xg, xo), 1e-8, outer_gpu=int(ig.outer_iterations), outer_oracle=int(io.outer_iterations))
 
 
 # ---- reference-derived golden vectors (tests/golden/ref_prec_vectors.npz) through the C ABI ------
 # The same comparisons pass for the CPU oracle (tests/test_reference_pinning.py, bit-identical) and
 # the CUDA library matches the oracle on these inputs (test_gpu_parity), so these are expected to
 # pass; they were written after the last GPU run of round 1, hence non-strict xfail.
-@pytest.mark.xfail(strict=False, reason="written after the last GPU run of round 1")
 @pytest.mark.parametrize("name", [n for n in REF_CASES if n in P.CASES])
 def test_cuda_preconditioner_reproduces_the_reference_vectors(name, oracle_mod):
     from .test_gpu_parity import _self_sensitivity
@@ -40,10 +42,9 @@ def test_cuda_preconditioner_reproduces_the_reference_vectors(name, oracle_mod):
     v, _ = gpu.apply_prec(u)
     # reproducibility floor of the inner CG trajectories (see test_gpu_parity._self_sensitivity)
     tol = max(1e-12, 50 * _self_sensitivity(lambda w: ora.apply_prec(w)[0], u, 2))
-    assert P.relerr(v, GOLD[f"{name}/v_ref"]) < tol
+    PL.check("apply_prec vs golden v_ref (reference header)", P.relerr(v, GOLD[f"{name}/v_ref"]), tol)
 
 
-@pytest.mark.xfail(strict=False, reason="written after the last GPU run of round 1")
 @pytest.mark.parametrize("name", ["laplace_diag", "laplace_exact", "stokes2d_exact", "stokes2d_diag", "stokes3d_diag",
                                   "elliptic_modified", "elliptic_ideal", "elasticity", "stokes2d_node"])
 def test_cuda_with_tight_inner_solves_matches_exact_reference_vectors(name):
@@ -64,37 +65,37 @@ def test_cuda_with_tight_inner_solves_matches_exact_reference_vectors(name):
 
     prob, ctx = tight_context(make, name)
     v, _ = ctx.apply_prec(P.rand(prob.n_dofs, 13))
-    assert P.relerr(v, GOLD[f"{name}/v_exact"]) < 1e-8
+    PL.check("apply_prec (tight inner solves) vs golden v_exact", P.relerr(v, GOLD[f"{name}/v_exact"]), 1e-8)
 
 
-# ---- opt-in dense W^-1 (FDAL_DENSE_WINV=1): exact mass inverses of a small multiplier space as one
-# L2-resident GEMV instead of the single-CTA PCG.  Compiled, never yet run on a GPU.
-@pytest.mark.xfail(strict=False, reason="opt-in path written after the last GPU run of round 1")
+# ---- exact W^-1 of a small multiplier space: one L2-resident dense GEMV (default for m <= 4096) or the
+# single-CTA Jacobi-PCG (FDAL_DENSE_WINV=0, and always for larger m)
+@pytest.mark.parametrize("dense", ["1", "0"])
 @pytest.mark.parametrize("name", ["laplace_exact", "laplace_opform", "stokes2d_exact", "elliptic_modified", "elliptic_ideal",
                                   "elasticity"])
-def test_dense_winv_path(name, oracle_mod, monkeypatch):
+def test_exact_winv_paths(name, dense, oracle_mod, monkeypatch):
     from fictitious_domain_al_preconditioners_b200 import ALContext
     from fictitious_domain_al_preconditioners_b200 import synthetic as syn
 
-    monkeypatch.setenv("FDAL_DENSE_WINV", "1")
+    monkeypatch.setenv("FDAL_DENSE_WINV", dense)
     prob, H = P.get(name)
     gpu = syn.setup_context(ALContext(prob.config), prob, H)
     ora = syn.setup_context(oracle_mod.OracleContext(prob.config), prob, H, oracle=True)
     x = P.rand(prob.sizes[-1], 4)
-    assert P.relerr(gpu.apply_winv(x), ora.apply_winv(x)) < 1e-12
+    PL.check("apply_winv", P.relerr(gpu.apply_winv(x), ora.apply_winv(x)), 1e-12)
     z = P.rand(prob.sizes[0], 3)
-    assert P.relerr(gpu.apply_aug(z), ora.apply_aug(z)) < 1e-12
+    PL.check("apply_aug", P.relerr(gpu.apply_aug(z), ora.apply_aug(z)), 1e-12)
     rhs = P.rhs_of(ora, prob)
     xg, ig = gpu.solve(rhs)
     xo, io = ora.solve(rhs)
     assert abs(ig.outer_iterations - io.outer_iterations) <= 1
 
 
-# ---- BSR kernel with four blocks per lane in flight (FDAL_BSR_UNROLL=4): 56 registers (B=2) /
-# 94 (B=3); ptxas batches ~20 loads in front of the first FMA.  Compiled, never run on a GPU.
-@pytest.mark.xfail(strict=False, reason="opt-in kernel variant written after the last GPU run of round 1")
+# ---- both BSR kernel variants on every block size: one block per lane, and four blocks per lane in flight
+# with the next step's row pointers and the epilogue operands fetched ahead (default for 2x2 blocks)
+@pytest.mark.parametrize("unroll", ["1", "4"])
 @pytest.mark.parametrize("name", ["stokes2d_node", "stokes3d_node", "elasticity"])
-def test_bsr_unroll4_variant(name, oracle_mod, monkeypatch):
+def test_bsr_kernel_variants(name, unroll, oracle_mod, monkeypatch):
     import copy
 
     import numpy as np
@@ -103,7 +104,7 @@ def test_bsr_unroll4_variant(name, oracle_mod, monkeypatch):
     from fictitious_domain_al_preconditioners_b200 import partition as part
     from fictitious_domain_al_preconditioners_b200 import synthetic as syn
 
-    monkeypatch.setenv("FDAL_BSR_UNROLL", "4")
+    monkeypatch.setenv("FDAL_BSR_UNROLL", unroll)
     prob, H = P.get(name)
     lp = part.distribute_problem(prob, H, 0, 1)
     cfg = copy.deepcopy(prob.config)
@@ -111,13 +112,13 @@ def test_bsr_unroll4_variant(name, oracle_mod, monkeypatch):
     gpu = part.setup_local_context(ALContext(cfg), lp)
     ora = syn.setup_context(oracle_mod.OracleContext(prob.config), prob, H, oracle=True)
     X = P.rand(prob.n_dofs, 5)
-    assert P.relerr(lp.gather([gpu.apply_system(lp.scatter(X))]), ora.apply_system(X)) < 1e-12
+    PL.check("apply_system", P.relerr(lp.gather([gpu.apply_system(lp.scatter(X))]), ora.apply_system(X)), 1e-12)
     n0 = prob.sizes[0]
     r = P.rand(n0, 7)
     rpad = np.concatenate([r, np.zeros(prob.n_dofs - n0)])
     z = gpu.apply_amg(lp.scatter(rpad)[:n0])
     zfull = lp.gather([np.concatenate([z, np.zeros(prob.n_dofs - n0)])])[:n0]
-    assert P.relerr(zfull, ora.apply_amg(r)) < 1e-12
+    PL.check("apply_amg", P.relerr(zfull, ora.apply_amg(r)), 1e-12)
     rhs = P.rhs_of(ora, prob)
     xg, ig = gpu.solve(lp.scatter(rhs))
     xo, io = ora.solve(rhs)
@@ -126,7 +127,6 @@ def test_bsr_unroll4_variant(name, oracle_mod, monkeypatch):
 
 # ---- the reference-side binding (include/fdal_dealii.h) + the reference's own preconditioner classes,
 # bound to the CUDA library (oracle/_ref/libadapter_cuda.so, prebuilt in the development container)
-@pytest.mark.xfail(strict=False, reason="written after the last GPU run of round 1")
 @pytest.mark.parametrize("name", ["laplace_diag", "stokes2d_exact", "stokes2d_minres", "elliptic_modified", "elliptic_ideal"])
 def test_reference_classes_on_the_cuda_library(name, oracle_mod):
     import numpy as np
@@ -144,31 +144,9 @@ def test_reference_classes_on_the_cuda_library(name, oracle_mod):
     assert st == 0
     v_gpu, _ = gpu.apply_prec(u)
     tol = max(1e-12, 50 * _self_sensitivity(lambda w: ora.apply_prec(w)[0], u, 2))
-    assert P.relerr(v_ref, v_gpu) < tol
-    assert P.relerr(v_ref, ora.apply_prec(u)[0]) < tol
+    PL.check("reference class on the CUDA library vs fdal_apply_prec", P.relerr(v_ref, v_gpu), tol)
+    PL.check("reference class on the CUDA library vs oracle", P.relerr(v_ref, ora.apply_prec(u)[0]), tol)
     rhs = P.rhs_of(ora, prob)
     xa, infa, st = ac.solve(lib, gpu, rhs)
     x, info = gpu.solve(rhs)
     assert st == 0 and infa.outer_iterations == info.outer_iterations and np.array_equal(xa, x)
-
-
-# ---- scalar CSR kernels with next-row-pointer and epilogue-operand prefetch (FDAL_SPMV_PF=1)
-@pytest.mark.xfail(strict=False, reason="opt-in kernel variant written after the last GPU run of round 1")
-@pytest.mark.parametrize("name", ["laplace_diag", "stokes2d_diag", "elliptic_modified", "elliptic_ideal"])
-def test_csr_prefetch_variant(name, oracle_mod, monkeypatch):
-    from fictitious_domain_al_preconditioners_b200 import ALContext
-    from fictitious_domain_al_preconditioners_b200 import synthetic as syn
-
-    monkeypatch.setenv("FDAL_SPMV_PF", "1")
-    prob, H = P.get(name)
-    gpu = syn.setup_context(ALContext(prob.config), prob, H)
-    ora = syn.setup_context(oracle_mod.OracleContext(prob.config), prob, H, oracle=True)
-    X = P.rand(prob.n_dofs, 5)
-    assert P.relerr(gpu.apply_system(X), ora.apply_system(X)) < 1e-12
-    r = P.rand(prob.sizes[0], 7)
-    assert P.relerr(gpu.apply_amg(r), ora.apply_amg(r)) < 1e-12
-    assert P.relerr(gpu.apply_aug(r), ora.apply_aug(r)) < 1e-12
-    rhs = P.rhs_of(ora, prob)
-    xg, ig = gpu.solve(rhs)
-    xo, io = ora.solve(rhs)
-    assert abs(ig.outer_iterations - io.outer_iterations) <= 1
