@@ -294,11 +294,13 @@ def build_hierarchy(
         cnt = np.bincount(agg[live], minlength=n_agg).astype(np.float64)
         T = sp.csr_matrix((1.0 / np.sqrt(cnt[agg[live]]), (live, agg[live])), shape=(n, n_agg))
         AT = _spgemm(A, T)
+        t0 = time.perf_counter()
         P = (T - (omega / lam) * (sp.diags(inv_diag) @ AT)).tocsr()
         del AT
         P.sort_indices()
         R = P.T.tocsr()
         R.sort_indices()
+        _log(f"  P, R: {time.perf_counter()-t0:.2f}s")
         Ac = _spgemm(R, _spgemm(A, P))
         Ac.sort_indices()
         L.P, L.R = P, R

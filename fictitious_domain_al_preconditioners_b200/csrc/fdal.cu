@@ -131,9 +131,15 @@ struct DevCsr {
   double *halo_buf = nullptr, *send_buf = nullptr;  // NCCL fallback only
   int *send_idx = nullptr;
   std::vector<int> send_counts, recv_counts;
+  // merge-path variant (k_spmv_merge): chosen at upload for matrices the row-group kernel cannot spread
+  // over the GPU (few rows, or very uneven rows); linear epilogues only
+  bool use_merge = false;
+  int merge_tiles = 0;
+  int *carry_row = nullptr;
+  double *carry_val = nullptr;
   int chan = -1;            // index into fdal_ctx::chans (peer-channel mode)
   int *order = nullptr;     // chunk order: interior chunks first (peer-channel mode)
-  int n_interior = 0;
+  int n_interior = 0, n_chunks = 0;
 };
 
 struct AmgLevel {
@@ -415,6 +421,7 @@ static int build_chunk_order(fdal_ctx *c, const HostCsr &h, DevCsr &d) {
   for (int64_t q = 0; q < nchunks; ++q)
     if (!bnd[(size_t)q]) order.push_back((int)q);
   d.n_interior = (int)order.size();
+  d.n_chunks = (int)nchunks;
   for (int64_t q = 0; q < nchunks; ++q)
     if (bnd[(size_t)q]) order.push_back((int)q);
   int st;
@@ -450,6 +457,21 @@ static int upload_csr(fdal_ctx *c, const HostCsr &h, DevCsr &d, int bsr_b = 1) {
   if (bsr_b > 1 && !getenv("FDAL_NO_BSR")) {
     bool done = false;
     if ((st = build_bsr(c, h, bsr_b, d, &done))) return st;
+  }
+  if (!d.use_bsr && !h.has_plan && h.nr > 0 && h.nnz > 0) {
+    // merge-path variant: when the row groups of k_spmv would fill less than half of the GPU's thread
+    // slots, or when one row is far longer than the average (FDAL_MERGE=1 / 0: always / never)
+    int maxlen = 0;
+    for (int64_t i = 0; i < h.nr; ++i) maxlen = std::max(maxlen, h.rp[i + 1] - h.rp[i]);
+    const double avg = (double)h.nnz / (double)h.nr;
+    bool want = (h.nnz >= 200000 && (double)h.nr * d.d.tpr < 0.5 * c->sms * 2048.0) || (h.nnz >= 1000000 && maxlen > 64.0 * avg);
+    if (const char *e = getenv("FDAL_MERGE")) want = atoi(e) > 0;
+    if (want) {
+      d.merge_tiles = (int)((h.nr + h.nnz + kMergeTile - 1) / kMergeTile);
+      if ((st = dmalloc(c, &d.carry_row, (size_t)d.merge_tiles))) return st;
+      if ((st = dmalloc(c, &d.carry_val, (size_t)d.merge_tiles))) return st;
+      d.use_merge = true;
+    }
   }
   if (h.has_plan) {
     d.has_plan = true;
@@ -583,12 +605,18 @@ static void halo_exchange(fdal_ctx *c, const DevCsr &A, const double *x) {
   ncclResult_t r = n->GroupEnd();
   if (r != ncclSuccess && !c->fail) c->fail = FDAL_ERR_NCCL;
 }
-static inline XVec xv(const fdal_ctx *c, const DevCsr &A, const double *x) {
+// `grid`: CTAs of the launch.  In peer-channel mode the first g_int CTAs share the interior chunks,
+// the rest acquire the halo and share the boundary chunks (kernels.cuh: chunk_range)
+static inline XVec xv(const fdal_ctx *c, const DevCsr &A, const double *x, int *grid) {
   XVec X{x, A.halo_buf, A.n_owned};
   if (c->p2p && A.chan >= 0 && !c->chans[(size_t)A.chan].nb.empty()) {
     X.ch = c->chans[(size_t)A.chan].d_dev;
     X.order = A.order;
     X.n_interior = A.n_interior;
+    const int n_bnd = A.n_chunks - A.n_interior;
+    const int g_bnd = n_bnd > 0 ? std::max(1, std::min(n_bnd, std::max(*grid / 8, c->sms))) : 0;
+    X.g_int = A.n_interior > 0 ? std::max(1, std::min(A.n_interior, *grid)) : 0;
+    *grid = std::max(1, X.g_int + g_bnd);
   }
   return X;
 }
@@ -597,17 +625,22 @@ template <class Epi, bool TWO>
 static void spmv_bsr(fdal_ctx *c, const DevCsr &A, const double *x, const DevCsr *B2, const double *t2, Epi epi,
                      double *red_out) {
   const int tpr = A.bsr.tpr;
-  const int g = grid_rows(c, A.bsr.nbrows, tpr);
+  int g = grid_rows(c, A.bsr.nbrows, tpr);
   Reducer R = reducer(c, red_out, A.dist_rows);
-  XVec X = xv(c, A, x);
+  XVec X = xv(c, A, x, &g);
   CsrDev b2 = B2 ? B2->d : CsrDev();
   const int unroll = A.bsr_b == 2 ? c->bsr_unroll2 : c->bsr_unroll3;
-#define FDAL_BSR_LAUNCH(BB, TT)                                                               \
-  do {                                                                                        \
-    if (unroll >= 4)                                                                          \
-      k_bsr_spmv<BB, TT, Epi, TWO, 4><<<g, kBlock, 0, c->stream>>>(A.bsr, X, b2, t2, epi, R); \
-    else                                                                                      \
-      k_bsr_spmv<BB, TT, Epi, TWO, 1><<<g, kBlock, 0, c->stream>>>(A.bsr, X, b2, t2, epi, R); \
+#define FDAL_BSR_LAUNCH(BB, TT)                                                                      \
+  do {                                                                                               \
+    if (X.ch) {                                                                                      \
+      if (unroll >= 4)                                                                               \
+        k_bsr_spmv<BB, TT, Epi, TWO, 4, true><<<g, kBlock, 0, c->stream>>>(A.bsr, X, b2, t2, epi, R); \
+      else                                                                                           \
+        k_bsr_spmv<BB, TT, Epi, TWO, 1, true><<<g, kBlock, 0, c->stream>>>(A.bsr, X, b2, t2, epi, R); \
+    } else if (unroll >= 4)                                                                          \
+      k_bsr_spmv<BB, TT, Epi, TWO, 4><<<g, kBlock, 0, c->stream>>>(A.bsr, X, b2, t2, epi, R);        \
+    else                                                                                             \
+      k_bsr_spmv<BB, TT, Epi, TWO, 1><<<g, kBlock, 0, c->stream>>>(A.bsr, X, b2, t2, epi, R);        \
   } while (0)
   if (A.bsr_b == 2) {
     switch (tpr) {
@@ -647,26 +680,37 @@ static void spmv(fdal_ctx *c, const DevCsr &A, const double *x, Epi epi, double 
     spmv_bsr<Epi, false>(c, A, x, nullptr, nullptr, epi, red_out);
     return;
   }
-  const int g = grid_rows(c, A.d.nrows, A.d.tpr);
-  Reducer R = reducer(c, red_out, A.dist_rows);
-  XVec X = xv(c, A, x);
-  if (c->spmv_unroll > 1) {
-    switch (A.d.tpr) {
-      case 2: k_spmv<2, Epi, 4><<<g, kBlock, 0, c->stream>>>(A.d, X, epi, R); break;
-      case 4: k_spmv<4, Epi, 4><<<g, kBlock, 0, c->stream>>>(A.d, X, epi, R); break;
-      case 8: k_spmv<8, Epi, 4><<<g, kBlock, 0, c->stream>>>(A.d, X, epi, R); break;
-      case 16: k_spmv<16, Epi, 4><<<g, kBlock, 0, c->stream>>>(A.d, X, epi, R); break;
-      default: k_spmv<32, Epi, 4><<<g, kBlock, 0, c->stream>>>(A.d, X, epi, R); break;
-    }
-  } else {
-    switch (A.d.tpr) {
-      case 2: k_spmv<2, Epi><<<g, kBlock, 0, c->stream>>>(A.d, X, epi, R); break;
-      case 4: k_spmv<4, Epi><<<g, kBlock, 0, c->stream>>>(A.d, X, epi, R); break;
-      case 8: k_spmv<8, Epi><<<g, kBlock, 0, c->stream>>>(A.d, X, epi, R); break;
-      case 16: k_spmv<16, Epi><<<g, kBlock, 0, c->stream>>>(A.d, X, epi, R); break;
-      default: k_spmv<32, Epi><<<g, kBlock, 0, c->stream>>>(A.d, X, epi, R); break;
+  if constexpr (std::is_same<Epi, EpiAssign>::value || std::is_same<Epi, EpiAdd>::value) {
+    if (A.use_merge && !red_out) {
+      k_spmv_merge<<<A.merge_tiles, kBlock, 0, c->stream>>>(A.d, x, epi.alpha, std::is_same<Epi, EpiAdd>::value ? 1 : 0,
+                                                            epi.y, A.carry_row, A.carry_val);
+      k_spmv_merge_fixup<<<std::max(1, std::min((A.merge_tiles + kBlock - 1) / kBlock, c->sms)), kBlock, 0, c->stream>>>(
+          A.merge_tiles, A.d.nrows, epi.alpha, A.carry_row, A.carry_val, epi.y);
+      c->launches += 2;
+      launch_check(c);
+      return;
     }
   }
+  int g = grid_rows(c, A.d.nrows, A.d.tpr);
+  Reducer R = reducer(c, red_out, A.dist_rows);
+  XVec X = xv(c, A, x, &g);
+#define FDAL_CSR_LAUNCH(TT)                                                         \
+  do {                                                                              \
+    if (X.ch)                                                                       \
+      k_spmv<TT, Epi, 4, true><<<g, kBlock, 0, c->stream>>>(A.d, X, epi, R);        \
+    else if (c->spmv_unroll > 1)                                                    \
+      k_spmv<TT, Epi, 4><<<g, kBlock, 0, c->stream>>>(A.d, X, epi, R);              \
+    else                                                                            \
+      k_spmv<TT, Epi><<<g, kBlock, 0, c->stream>>>(A.d, X, epi, R);                 \
+  } while (0)
+  switch (A.d.tpr) {
+    case 2: FDAL_CSR_LAUNCH(2); break;
+    case 4: FDAL_CSR_LAUNCH(4); break;
+    case 8: FDAL_CSR_LAUNCH(8); break;
+    case 16: FDAL_CSR_LAUNCH(16); break;
+    default: FDAL_CSR_LAUNCH(32); break;
+  }
+#undef FDAL_CSR_LAUNCH
   c->launches++;
   launch_check(c);
   finish_scalar(c, red_out, red_out ? 1 : 0, A.dist_rows);
@@ -691,26 +735,26 @@ static void spmv2(fdal_ctx *c, const DevCsr &A, const double *x, const DevCsr &C
     spmv_bsr<Epi, true>(c, A, x, &Ct, t, epi, red_out);
     return;
   }
-  const int g = grid_rows(c, A.d.nrows, A.d.tpr);
+  int g = grid_rows(c, A.d.nrows, A.d.tpr);
   Reducer R = reducer(c, red_out, A.dist_rows);
-  XVec X = xv(c, A, x);
-  if (c->spmv_unroll > 1) {
-    switch (A.d.tpr) {
-      case 2: k_spmv2<2, Epi, 4><<<g, kBlock, 0, c->stream>>>(A.d, X, Ct.d, t, epi, R); break;
-      case 4: k_spmv2<4, Epi, 4><<<g, kBlock, 0, c->stream>>>(A.d, X, Ct.d, t, epi, R); break;
-      case 8: k_spmv2<8, Epi, 4><<<g, kBlock, 0, c->stream>>>(A.d, X, Ct.d, t, epi, R); break;
-      case 16: k_spmv2<16, Epi, 4><<<g, kBlock, 0, c->stream>>>(A.d, X, Ct.d, t, epi, R); break;
-      default: k_spmv2<32, Epi, 4><<<g, kBlock, 0, c->stream>>>(A.d, X, Ct.d, t, epi, R); break;
-    }
-  } else {
-    switch (A.d.tpr) {
-      case 2: k_spmv2<2, Epi><<<g, kBlock, 0, c->stream>>>(A.d, X, Ct.d, t, epi, R); break;
-      case 4: k_spmv2<4, Epi><<<g, kBlock, 0, c->stream>>>(A.d, X, Ct.d, t, epi, R); break;
-      case 8: k_spmv2<8, Epi><<<g, kBlock, 0, c->stream>>>(A.d, X, Ct.d, t, epi, R); break;
-      case 16: k_spmv2<16, Epi><<<g, kBlock, 0, c->stream>>>(A.d, X, Ct.d, t, epi, R); break;
-      default: k_spmv2<32, Epi><<<g, kBlock, 0, c->stream>>>(A.d, X, Ct.d, t, epi, R); break;
-    }
+  XVec X = xv(c, A, x, &g);
+#define FDAL_CSR2_LAUNCH(TT)                                                               \
+  do {                                                                                     \
+    if (X.ch)                                                                              \
+      k_spmv2<TT, Epi, 4, true><<<g, kBlock, 0, c->stream>>>(A.d, X, Ct.d, t, epi, R);     \
+    else if (c->spmv_unroll > 1)                                                           \
+      k_spmv2<TT, Epi, 4><<<g, kBlock, 0, c->stream>>>(A.d, X, Ct.d, t, epi, R);           \
+    else                                                                                   \
+      k_spmv2<TT, Epi><<<g, kBlock, 0, c->stream>>>(A.d, X, Ct.d, t, epi, R);              \
+  } while (0)
+  switch (A.d.tpr) {
+    case 2: FDAL_CSR2_LAUNCH(2); break;
+    case 4: FDAL_CSR2_LAUNCH(4); break;
+    case 8: FDAL_CSR2_LAUNCH(8); break;
+    case 16: FDAL_CSR2_LAUNCH(16); break;
+    default: FDAL_CSR2_LAUNCH(32); break;
   }
+#undef FDAL_CSR2_LAUNCH
   c->launches++;
   launch_check(c);
   finish_scalar(c, red_out, red_out ? 1 : 0, A.dist_rows);
@@ -1087,7 +1131,13 @@ static void couple_phase1(fdal_ctx *c, const double *x, double a, const double *
     return;
   }
   if (c->cfg.winv_mode == FDAL_WINV_DIAG) {
-    spmv(c, C, x, EpiCouple{t, c->d_winv, a, add, y1});
+    if (C.use_merge) {  // few, long rows: merge-path C x, then the element-wise coupling epilogue
+      spmv(c, C, x, EpiAssign{c->t_m1, 1.0});
+      k_couple_elem<<<grid_elems(c, c->m), kBlock, 0, c->stream>>>((int)c->m, c->t_m1, c->d_winv, a, add, y1, t);
+      c->launches++;
+    } else {
+      spmv(c, C, x, EpiCouple{t, c->d_winv, a, add, y1});
+    }
   } else {
     spmv(c, C, x, EpiCouple{c->t_m1, nullptr, 1.0, nullptr, y1});
     apply_winv_scaled(c, a, c->t_m1, t, add);
@@ -2204,14 +2254,30 @@ int fdal_finalize(fdal_ctx *c) {
   if (!c->hmat[FDAL_MAT_C].set) host_transpose(c->hmat[FDAL_MAT_CT], c->hmat[FDAL_MAT_C]);
   if (is_stokes(c) && !c->hmat[FDAL_MAT_B].set) host_transpose(c->hmat[FDAL_MAT_BT], c->hmat[FDAL_MAT_B]);
   for (int id = 0; id < FDAL_MAT_COUNT; ++id)
-    if (c->hmat[id].set) {
+    if (c->hmat[id].set)
       if ((st = upload_csr(c, c->hmat[id], c->dmat[id], id == FDAL_MAT_A ? c->cfg.block_size : 1))) return st;
-      // host copy no longer needed
-      HostCsr &h = c->hmat[id];
-      std::vector<int>().swap(h.ci);
-      std::vector<double>().swap(h.v);
-      std::vector<int>().swap(h.rp);
-    }
+  // Ct rides along in the row pass over A (fused augmented apply): flag the row chunks of A in which Ct
+  // has any entry, so the other ~99 % of the chunks never look at Ct's row pointers
+  {
+    const DevCsr &A = c->dmat[FDAL_MAT_A];
+    const HostCsr &hct = c->hmat[FDAL_MAT_CT];
+    const int64_t rpb = (int64_t)(kBlock / (A.use_bsr ? A.bsr.tpr : A.d.tpr)) * (A.use_bsr ? A.bsr_b : 1);
+    const int64_t nchunks = (hct.nr + rpb - 1) / rpb;
+    std::vector<unsigned char> any((size_t)std::max<int64_t>(nchunks, 1), 0);
+    for (int64_t q = 0; q < nchunks; ++q)
+      any[(size_t)q] = hct.rp[(size_t)std::min<int64_t>(hct.nr, (q + 1) * rpb)] > hct.rp[(size_t)(q * rpb)];
+    unsigned char *d_any = nullptr;
+    if ((st = dmalloc(c, &d_any, any.size()))) return st;
+    CU(cudaMemcpyAsync(d_any, any.data(), any.size(), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (!getenv("FDAL_NO_CHUNK_FLAGS")) c->dmat[FDAL_MAT_CT].d.chunk_any = d_any;
+  }
+  for (int id = 0; id < FDAL_MAT_COUNT; ++id) {  // host copies no longer needed
+    HostCsr &h = c->hmat[id];
+    std::vector<int>().swap(h.ci);
+    std::vector<double>().swap(h.v);
+    std::vector<int>().swap(h.rp);
+  }
   for (int id : {FDAL_MAT_A, FDAL_MAT_BT, FDAL_MAT_B, FDAL_MAT_MP}) c->dmat[id].dist_rows = D;
   // AMG
   if (c->cfg.inner_prec == FDAL_PREC_AMG) {

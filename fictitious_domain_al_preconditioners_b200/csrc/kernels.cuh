@@ -32,6 +32,11 @@ struct CsrDev {
   const int *ci = nullptr;
   const double *v = nullptr;
   int tpr = 8;  // threads per row
+  // as the SECOND matrix of a fused two-matrix pass (Ct beside A): one flag per row chunk of the
+  // first matrix, 0 = none of the chunk's rows has an entry here (almost every chunk of Ct: the
+  // immersed body touches a thin band of background rows), so the pass skips this matrix's row
+  // pointers for the whole chunk.  nullptr: look at every row.
+  const unsigned char *chunk_any = nullptr;
 };
 
 // x vector with an optional halo part (multi-GPU): columns [0,n_owned) are local,
@@ -81,35 +86,42 @@ struct XVec {
   const double *x;
   const double *halo;
   int n_owned;
-  // multi-GPU with peer channels: halo = ch->recv + (epoch & 1) * cap, rows are walked in
-  // `order` (interior chunks first) and a block acquires the halo before its first chunk
-  // at position >= n_interior.  ch == nullptr: single GPU or NCCL-filled halo buffer.
+  // multi-GPU with peer channels: halo = ch->recv + (epoch & 1) * cap.  The row chunks are walked in
+  // `order` (the n_interior chunks without halo columns first).  The first g_int CTAs of the grid share
+  // the interior chunks and never wait; the remaining CTAs acquire the halo once, before their loop, and
+  // share the boundary chunks — the peers' pushes overlap the interior rows and no barrier sits inside
+  // the row loop (a barrier there stops ptxas from unrolling the row walk: -13 % on the 3-D V-cycle).
+  // ch == nullptr: single GPU or NCCL-filled halo buffer.
   const ChanDev *ch = nullptr;
   const int *order = nullptr;
   int n_interior = 0;
+  int g_int = 0;
 };
+// ONE load instruction for owned and halo entries (a select on the address, no branch), through the
+// read-only path like every other operand of the row walk.  The halo slot is filled by the peers
+// before the flag this block acquires in chunk_range(), no thread of the kernel touches a halo address
+// before that acquire (interior chunks have no halo columns), and L1 does not survive kernel
+// boundaries — so no stale line can be resident when the first ld.global.nc of a halo entry issues.
 __device__ __forceinline__ double xload(const XVec &X, int c) {
-  return c < X.n_owned ? __ldg(X.x + c) : X.halo[c - X.n_owned];
+  const double *p = c < X.n_owned ? X.x + c : X.halo + (c - X.n_owned);
+  return __ldg(p);
 }
-// per-block state of a halo consumer
-struct HaloState {
-  unsigned long long e = 0;
-  bool armed = false, done = false;
+// chunk positions [p, pend) with stride `stride` of this CTA; boundary CTAs acquire the halo here
+struct ChunkRange {
+  int p, pend, stride;
 };
-__device__ __forceinline__ void halo_begin(XVec &X, HaloState &h) {
-  if (X.ch) {
-    h.e = *X.ch->epoch;  // written by the push kernel that precedes this kernel in stream order
-    X.halo = X.ch->recv + (size_t)(h.e & 1ull) * X.ch->cap;
-    h.armed = true;
-  }
+template <bool DIST>
+__device__ __forceinline__ ChunkRange chunk_range(XVec &X, int nchunks) {
+  if (!DIST) return ChunkRange{(int)blockIdx.x, nchunks, (int)gridDim.x};
+  const unsigned long long e = *X.ch->epoch;  // written by the push kernel that precedes this kernel in stream order
+  X.halo = X.ch->recv + (size_t)(e & 1ull) * X.ch->cap;
+  if ((int)blockIdx.x < X.g_int) return ChunkRange{(int)blockIdx.x, X.n_interior, X.g_int};
+  chan_wait(*X.ch, e);
+  return ChunkRange{X.n_interior + ((int)blockIdx.x - X.g_int), nchunks, (int)gridDim.x - X.g_int};
 }
-// p: chunk position (block-uniform).  Returns the chunk to process.
-__device__ __forceinline__ long long halo_chunk(const XVec &X, HaloState &h, long long p) {
-  if (h.armed && !h.done && p >= X.n_interior) {
-    chan_wait(*X.ch, h.e);
-    h.done = true;
-  }
-  return X.order ? (long long)__ldg(X.order + p) : p;
+template <bool DIST>
+__device__ __forceinline__ int chunk_at(const XVec &X, int p) {
+  return DIST ? __ldg(X.order + p) : p;
 }
 
 // ---- in-kernel reduction: block partial -> last block sums partials in fixed order
@@ -386,18 +398,17 @@ __device__ __forceinline__ double row_partial(const CsrDev &A, const XVec &X, in
   return s;
 }
 
-template <int TPR, class Epi, int U = 1>
+template <int TPR, class Epi, int U = 1, bool DIST = false>
 __global__ void __launch_bounds__(kBlock) k_spmv(CsrDev A, XVec X, Epi epi, Reducer R) {
   __shared__ double smem[32];
   constexpr int rows_per_block = kBlock / TPR;
   const int lane = threadIdx.x & (TPR - 1);
   const int local_row = threadIdx.x / TPR;
   double contrib = 0.0;
-  HaloState hs;
-  halo_begin(X, hs);
-  const long long nchunks = ((long long)A.nrows + rows_per_block - 1) / rows_per_block;
-  for (long long p = blockIdx.x; p < nchunks; p += gridDim.x) {
-    const long long row = halo_chunk(X, hs, p) * rows_per_block + local_row;
+  const int nchunks = (A.nrows + rows_per_block - 1) / rows_per_block;
+  const ChunkRange cr = chunk_range<DIST>(X, nchunks);
+  for (int p = cr.p; p < cr.pend; p += cr.stride) {
+    const int row = chunk_at<DIST>(X, p) * rows_per_block + local_row;
     double s = 0.0;
     if (row < A.nrows) s = row_partial<TPR, U>(A, X, __ldg(A.rp + row), __ldg(A.rp + row + 1), lane);
 #pragma unroll
@@ -411,7 +422,7 @@ __global__ void __launch_bounds__(kBlock) k_spmv(CsrDev A, XVec X, Epi epi, Redu
 // Two CSR matrices with the same row partition are walked in one row pass, so A x
 // never goes to memory before the coupling term is added (K3).  t already carries
 // gamma * W^-1 C x (phase 1), and for the block system also + x1.
-template <int TPR, class Epi, int U = 1>
+template <int TPR, class Epi, int U = 1, bool DIST = false>
 __global__ void __launch_bounds__(kBlock) k_spmv2(CsrDev A, XVec X, CsrDev Ct, const double *__restrict__ t, Epi epi,
                                                    Reducer R) {
   __shared__ double smem[32];
@@ -419,14 +430,19 @@ __global__ void __launch_bounds__(kBlock) k_spmv2(CsrDev A, XVec X, CsrDev Ct, c
   const int lane = threadIdx.x & (TPR - 1);
   const int local_row = threadIdx.x / TPR;
   double contrib = 0.0;
-  HaloState hs;
-  halo_begin(X, hs);
-  const long long nchunks = ((long long)A.nrows + rows_per_block - 1) / rows_per_block;
-  for (long long p = blockIdx.x; p < nchunks; p += gridDim.x) {
-    const long long row = halo_chunk(X, hs, p) * rows_per_block + local_row;
+  const int nchunks = (A.nrows + rows_per_block - 1) / rows_per_block;
+  const ChunkRange cr = chunk_range<DIST>(X, nchunks);
+  for (int p = cr.p; p < cr.pend; p += cr.stride) {
+    const int chunk = chunk_at<DIST>(X, p);
+    const int row = chunk * rows_per_block + local_row;
+    const bool second = !Ct.chunk_any || __ldg(Ct.chunk_any + chunk);
     double s = 0.0;
     if (row < A.nrows) {
-      const int c0 = __ldg(Ct.rp + row), c1 = __ldg(Ct.rp + row + 1);
+      int c0 = 0, c1 = 0;
+      if (second) {
+        c0 = __ldg(Ct.rp + row);
+        c1 = __ldg(Ct.rp + row + 1);
+      }
       s = row_partial<TPR, U>(A, X, __ldg(A.rp + row), __ldg(A.rp + row + 1), lane);
       for (int k = c0 + lane; k < c1; k += TPR) s += __ldg(Ct.v + k) * __ldg(t + __ldg(Ct.ci + k));
     }
@@ -435,6 +451,91 @@ __global__ void __launch_bounds__(kBlock) k_spmv2(CsrDev A, XVec X, CsrDev Ct, c
     if (lane == 0 && row < A.nrows) contrib += epi((int)row, s);
   }
   if (Epi::kReduce) reduce_finalize(contrib, R, 0, 1, smem);
+}
+
+// ---- merge-path CSR SpMV (Merrill & Garland, SC'16):  y = alpha A x  or  y += alpha A x ----------
+// The merge of the nrows row-end offsets with the nnz non-zero indices is cut into equal pieces of
+// kMergeIPT items per thread, whatever the row lengths: a matrix with fewer rows than the GPU has
+// row groups (C = Ct^T: one row per multiplier, a few thousand rows) or with very uneven rows
+// (restriction operators, constraint rows) still spreads evenly over all SMs, where the row-group
+// kernel k_spmv leaves lanes and SMs idle.  A thread walks its piece sequentially — consume a
+// non-zero, or finish a row — and hands the unfinished tail of its last row on as a carry.  Carries are
+// folded in a fixed order (deterministic, no atomics): inside the CTA through shared memory, across CTAs
+// by k_spmv_merge_fixup.  Only linear epilogues (assign / add), because a row's sum is completed after
+// the pass.
+constexpr int kMergeIPT = 8;                      // merge items per thread
+constexpr int kMergeTile = kMergeIPT * kBlock;    // merge items per CTA
+
+__global__ void __launch_bounds__(kBlock) k_spmv_merge(CsrDev A, const double *__restrict__ x, double alpha, int add,
+                                                        double *__restrict__ y, int *__restrict__ carry_row,
+                                                        double *__restrict__ carry_val) {
+  __shared__ int s_row[kBlock];
+  __shared__ double s_val[kBlock];
+  const long long n_items = (long long)A.nrows + A.nnz;
+  const long long d0 = min((long long)blockIdx.x * kMergeTile + (long long)threadIdx.x * kMergeIPT, n_items);
+  // split point of diagonal d0: i rows finished, j non-zeros consumed, i + j = d0
+  long long lo = max(0ll, d0 - A.nnz), hi = min(d0, (long long)A.nrows);
+  while (lo < hi) {
+    const long long mid = (lo + hi) >> 1;
+    if ((long long)__ldg(A.rp + mid + 1) <= d0 - mid - 1)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  int row = (int)lo;
+  long long j = d0 - lo;
+  double run = 0.0;
+  int row_end = row < A.nrows ? __ldg(A.rp + row + 1) : 0;
+#pragma unroll
+  for (int s = 0; s < kMergeIPT; ++s) {
+    if (d0 + s >= n_items || row >= A.nrows) break;
+    if (j < row_end) {
+      run += __ldg(A.v + j) * x[__ldg(A.ci + j)];
+      ++j;
+    } else {
+      // this thread finishes the row: its own part now, the earlier threads' carries in the fix-up
+      y[row] = add ? y[row] + alpha * run : alpha * run;
+      run = 0.0;
+      ++row;
+      row_end = row < A.nrows ? __ldg(A.rp + row + 1) : 0;
+    }
+  }
+  s_row[threadIdx.x] = row;
+  s_val[threadIdx.x] = run;
+  __syncthreads();
+  // carries with the same row form a run of consecutive threads: its last thread folds the run
+  const bool last_of_run = threadIdx.x == kBlock - 1 || s_row[threadIdx.x + 1] != row;
+  if (last_of_run && row < A.nrows) {
+    double tot = 0.0;
+    int t = threadIdx.x;
+    while (t >= 0 && s_row[t] == row) --t;
+    for (++t; t <= (int)threadIdx.x; ++t) tot += s_val[t];  // ascending thread order: fixed summation order
+    if (threadIdx.x == kBlock - 1) {
+      carry_row[blockIdx.x] = row;  // the row continues in the next CTA (or ends exactly here: then a later
+      carry_val[blockIdx.x] = tot;  // thread has written / will write its tail and the fix-up adds this)
+    } else {
+      y[row] += alpha * tot;  // the row was finished by thread threadIdx.x + 1 of this CTA (visible after the barrier)
+    }
+  } else if (threadIdx.x == kBlock - 1) {
+    carry_row[blockIdx.x] = A.nrows;  // nothing to carry
+    carry_val[blockIdx.x] = 0.0;
+  }
+}
+// fold the CTA carries: CTAs whose carry belongs to the same row are consecutive
+__global__ void __launch_bounds__(kBlock) k_spmv_merge_fixup(int n_tiles, int nrows, double alpha,
+                                                              const int *__restrict__ carry_row,
+                                                              const double *__restrict__ carry_val,
+                                                              double *__restrict__ y) {
+  for (int b = blockIdx.x * kBlock + threadIdx.x; b < n_tiles; b += gridDim.x * kBlock) {
+    const int row = carry_row[b];
+    if (row >= nrows) continue;
+    if (b + 1 < n_tiles && carry_row[b + 1] == row) continue;  // not the last CTA of this row's run
+    int t = b;
+    while (t >= 0 && carry_row[t] == row) --t;
+    double tot = 0.0;
+    for (++t; t <= b; ++t) tot += carry_val[t];
+    y[row] += alpha * tot;
+  }
 }
 
 // ---- BSR SpMV for node-interleaved vector-valued blocks (Stokes velocity, elasticity) ----
@@ -454,7 +555,7 @@ struct BsrDev {
   int aos = 0;
 };
 
-template <int B, int TPR, class Epi, bool TWO, int U = 1>
+template <int B, int TPR, class Epi, bool TWO, int U = 1, bool DIST = false>
 __global__ void __launch_bounds__(kBlock) k_bsr_spmv(BsrDev A, XVec X, CsrDev C2, const double *__restrict__ t2, Epi epi,
                                                       Reducer R) {
   __shared__ double smem[32];
@@ -465,22 +566,21 @@ __global__ void __launch_bounds__(kBlock) k_bsr_spmv(BsrDev A, XVec X, CsrDev C2
   double contrib = 0.0;
   // U >= 4 (opt-in variant): the block-row pointers of the NEXT grid-stride step are fetched while
   // this step's blocks are in flight, which takes one DRAM latency out of every step's chain
-  HaloState hs;
-  halo_begin(X, hs);
-  const long long nchunks = ((long long)A.nbrows + rows_per_block - 1) / rows_per_block;
-  auto chunk_of = [&](long long p) { return X.order ? (long long)__ldg(X.order + p) : p; };
+  const int nchunks = (A.nbrows + rows_per_block - 1) / rows_per_block;
+  const ChunkRange cr = chunk_range<DIST>(X, nchunks);
   int k0n = 0, k1n = 0;
   if constexpr (U >= 4) {
-    if ((long long)blockIdx.x < nchunks) {
-      const long long I0 = chunk_of(blockIdx.x) * rows_per_block + local_row;
+    if (cr.p < cr.pend) {
+      const long long I0 = (long long)chunk_at<DIST>(X, cr.p) * rows_per_block + local_row;
       if (I0 < A.nbrows) {
         k0n = __ldg(A.rp + I0);
         k1n = __ldg(A.rp + I0 + 1);
       }
     }
   }
-  for (long long p = blockIdx.x; p < nchunks; p += gridDim.x) {
-    const long long I = halo_chunk(X, hs, p) * rows_per_block + local_row;
+  for (int p = cr.p; p < cr.pend; p += cr.stride) {
+    const int chunk = chunk_at<DIST>(X, p);
+    const long long I = (long long)chunk * rows_per_block + local_row;
     double s[B];
 #pragma unroll
     for (int r = 0; r < B; ++r) s[r] = 0.0;
@@ -490,9 +590,9 @@ __global__ void __launch_bounds__(kBlock) k_bsr_spmv(BsrDev A, XVec X, CsrDev C2
       if constexpr (U >= 4) {
         k0 = k0n;
         k1 = k1n;
-        const long long pn = p + gridDim.x;
-        if (pn < nchunks) {
-          const long long In = chunk_of(pn) * rows_per_block + local_row;
+        const int pn = p + cr.stride;
+        if (pn < cr.pend) {
+          const long long In = (long long)chunk_at<DIST>(X, pn) * rows_per_block + local_row;
           if (In < A.nbrows) {
             k0n = __ldg(A.rp + In);
             k1n = __ldg(A.rp + In + 1);
@@ -514,13 +614,12 @@ __global__ void __launch_bounds__(kBlock) k_bsr_spmv(BsrDev A, XVec X, CsrDev C2
           const int k = kk + u * TPR;
           const bool ok = k < nb;
           const int c = (ok ? __ldg(A.cj + k0 + k) : 0) * B;
-          const bool own = c < X.n_owned;
-          const double *xp = own ? X.x + c : X.halo + (c - X.n_owned);
+          const double *xp = c < X.n_owned ? X.x + c : X.halo + (c - X.n_owned);
 #pragma unroll
           for (int q = 0; q < B * B; ++q)
             a[u][q] = ok ? __ldg(vb + (size_t)k * (B * B) + q) : 0.0;
 #pragma unroll
-          for (int q = 0; q < B; ++q) xj[u][q] = ok ? (own ? __ldg(xp + q) : xp[q]) : 0.0;
+          for (int q = 0; q < B; ++q) xj[u][q] = ok ? __ldg(xp + q) : 0.0;
         }
 #pragma unroll
         for (int u = 0; u < U; ++u)
@@ -529,7 +628,7 @@ __global__ void __launch_bounds__(kBlock) k_bsr_spmv(BsrDev A, XVec X, CsrDev C2
 #pragma unroll
             for (int q = 0; q < B; ++q) s[r] += a[u][r * B + q] * xj[u][q];
       }
-      if (TWO) {
+      if (TWO && (!C2.chunk_any || __ldg(C2.chunk_any + chunk))) {
 #pragma unroll
         for (int r = 0; r < B; ++r) {
           const long long row = I * B + r;

@@ -303,6 +303,47 @@ def _csr(A):
     return A
 
 
+def add_low_rank_rows(A: sp.csr_matrix, S: sp.csr_matrix) -> sp.csr_matrix:
+    """A + S for a huge A and an S that only touches a few rows (the AL term gamma Ct W^-1 C lives on the
+    rows next to the immersed body): the untouched rows of A are copied as they are, only the touched rows
+    go through a sparse add — no sort / duplicate pass over the 10^9 entries of A (the general scipy
+    `A + S` followed by canonicalisation costs tens of seconds there)."""
+    A = A.tocsr()
+    S = sp.csr_matrix(S)
+    S.sum_duplicates()
+    S.sort_indices()
+    rows = np.nonzero(np.diff(S.indptr))[0]
+    if rows.size == 0 or rows.size > A.shape[0] // 2 or not A.has_sorted_indices:
+        return _csr(A + S)
+    sub = (A[rows] + S[rows]).tocsr()
+    sub.sort_indices()
+    cnt = np.diff(A.indptr).astype(np.int64)
+    cnt[rows] = np.diff(sub.indptr)
+    indptr = np.zeros(A.shape[0] + 1, dtype=np.int64)
+    np.cumsum(cnt, out=indptr[1:])
+    nnz = int(indptr[-1])
+    indices = np.empty(nnz, dtype=A.indices.dtype)
+    data = np.empty(nnz, dtype=np.float64)
+    # copy the untouched stretches between consecutive touched rows in bulk
+    r_prev = 0
+    for k, r in enumerate(np.append(rows, A.shape[0])):
+        if r > r_prev:  # rows [r_prev, r) unchanged
+            a0, a1 = int(A.indptr[r_prev]), int(A.indptr[r])
+            o0 = int(indptr[r_prev])
+            indices[o0:o0 + (a1 - a0)] = A.indices[a0:a1]
+            data[o0:o0 + (a1 - a0)] = A.data[a0:a1]
+        if r < A.shape[0]:
+            s0, s1 = int(sub.indptr[k]), int(sub.indptr[k + 1])
+            o0 = int(indptr[r])
+            indices[o0:o0 + (s1 - s0)] = sub.indices[s0:s1]
+            data[o0:o0 + (s1 - s0)] = sub.data[s0:s1]
+        r_prev = r + 1
+    out = sp.csr_matrix((data, indices, indptr if nnz >= 2**31 - 1 else indptr.astype(np.int32)), shape=A.shape)
+    out.has_sorted_indices = True
+    out.has_canonical_format = True
+    return out
+
+
 # ----------------------------------------------------------------------------- problem container
 @dataclass
 class Problem:
@@ -701,6 +742,9 @@ def stokes_immersed_boundary(
         A = apply_dirichlet(A, bnd)
         if node_major:
             A = _csr(A[node_order][:, node_order])
+    from .amg_setup import _log as _slog
+
+    _t1 = _time.perf_counter()
     Bblk = [-K({kk: (E if kk == c else F) for kk in dims}) for c in dims]
     B = _csr(sp.hstack(Bblk, format="csr"))
     Mp = _csr(kron_all([Mq1] * dim))
@@ -708,6 +752,8 @@ def stokes_immersed_boundary(
     if node_major:
         Bt = _csr(Bt[node_order])
     n_u, n_p = A.shape[0], Mp.shape[0]
+    _slog(f"B, Bt, Mp: {_time.perf_counter()-_t1:.2f}s")
+    _t1 = _time.perf_counter()
     # immersed boundary
     if dim == 2:
         if r_emb is None:
@@ -772,10 +818,13 @@ def stokes_immersed_boundary(
     else:
         cfg.winv_mode = b.WINV_EXACT_M_SQUARED
         cfg.mp_inv_mode = b.MPINV_EXACT
+    _slog(f"coupling blocks, rhs: {_time.perf_counter()-_t1:.2f}s")
+    _t1 = _time.perf_counter()
     if build_amg_matrix:
         # build_AMG_augmented_block: (grad,grad)+gamma(div,div) + gamma Ct diag(1/Mii^2) C
         # (utilities.h:112-331; the AL gamma is used for grad-div, SURVEY Q7 — equal here)
-        prob.amg_matrix[b.AMG_A11] = _csr(A + gamma * (Ct @ sp.diags(winv) @ Ct.T))
+        prob.amg_matrix[b.AMG_A11] = add_low_rank_rows(A, gamma * (Ct @ sp.diags(winv) @ Ct.T))
+        _slog(f"explicit augmented matrix: {_time.perf_counter()-_t1:.2f}s")
         prob.amg_theta[b.AMG_A11] = 0.02  # utilities.h:314
         comp = np.repeat(np.arange(dim, dtype=np.int32), ns)
         prob.amg_comp[b.AMG_A11] = comp[node_order] if node_major else comp
