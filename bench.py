@@ -52,6 +52,16 @@ def log(msg):
     sys.stderr.flush()
 
 
+T_START = time.perf_counter()
+# the driver gives every bench step a fixed wall-clock limit (870 s in the scaling run): both arms watch this
+# deadline and shorten the run (fewer timed solves, reported as such) rather than be killed without a line
+DEADLINE_S = float(os.environ.get("FDAL_BENCH_DEADLINE_S", "780"))
+
+
+def elapsed():
+    return time.perf_counter() - T_START
+
+
 METRIC = "outer_fgmres_solve_dofs_per_s"
 UNIT = "DoF/s"
 DEFAULT_WORKLOAD = "stokes3d_10M"
@@ -185,32 +195,71 @@ def run_reference(args, w, wname):
     prob, H = build_problem(w)
     t_setup = time.perf_counter() - t0
     log(f"reference arm: problem + hierarchy in {t_setup:.1f} s, {prob.n_dofs} DoFs")
-    ctx = syn.setup_context(oracle.OracleContext(prob.config, threads=cores), prob, H, oracle=True)
-    rhs = ctx.augment_rhs(prob.rhs) if prob.augment_rhs else prob.rhs
     budget = float(os.environ.get("FDAL_REF_BUDGET_S", "600"))
     times, infos, spent, n_warm = [], [], 0.0, 0
     want_warm = args.warmup
-    while len(times) < max(1, args.steps):
+    extrapolated = None
+    if prob.n_dofs > int(float(os.environ.get("FDAL_REF_PROBE_MIN_DOFS", "2e6"))):
+        # a complete solve of a problem this size takes minutes: time the first outer iterations to see whether
+        # it fits the step's wall-clock limit (own context, closed again: two oracle copies of the matrices
+        # would not fit the host memory beside the scipy originals)
+        import copy
+
+        cfg2 = copy.deepcopy(prob.config)
+        cfg2.outer.max_steps = 2
+        p2 = copy.copy(prob)
+        p2.config = cfg2
+        pctx = syn.setup_context(oracle.OracleContext(cfg2, threads=cores), p2, H, oracle=True)
+        prhs = pctx.augment_rhs(prob.rhs) if prob.augment_rhs else prob.rhs
+        t0 = time.perf_counter()
+        _, pinfo = pctx.solve(prhs, raise_on_failure=False)
+        t_probe = time.perf_counter() - t0
+        pctx.close()
+        del pctx
+        n_outer_gpu = int(os.environ.get("FDAL_EXPECTED_OUTER", "0")) or 12
+        predicted = t_probe / max(1, pinfo.outer_iterations) * n_outer_gpu
+        log(f"reference arm: probe of {pinfo.outer_iterations} outer iterations took {t_probe:.1f} s; a complete solve is "
+            f"predicted at {predicted:.0f} s, {DEADLINE_S - elapsed():.0f} s left before the deadline")
+        if predicted * 1.25 + 30 > DEADLINE_S - elapsed():
+            extrapolated = dict(t_probe=t_probe, outer_probe=int(pinfo.outer_iterations), inner_probe=int(pinfo.inner_iterations),
+                                n_outer=n_outer_gpu, predicted=predicted)
+    ctx = None
+    if extrapolated is None:
+        ctx = syn.setup_context(oracle.OracleContext(prob.config, threads=cores), prob, H, oracle=True)
+        rhs = ctx.augment_rhs(prob.rhs) if prob.augment_rhs else prob.rhs
+    while extrapolated is None and len(times) < max(1, args.steps):
         t0 = time.perf_counter()
         _, info = ctx.solve(rhs, raise_on_failure=False)
         dt = time.perf_counter() - t0
         spent += dt
         log(f"reference arm: complete solve in {dt:.2f} s ({info.outer_iterations} outer / {info.inner_iterations} inner)")
         # a warm-up solve is only affordable when a solve is short compared with the budget
-        if n_warm < want_warm and spent + dt * (1 + len(times)) < budget * 0.5:
+        if n_warm < want_warm and spent + dt * (1 + len(times)) < budget * 0.5 and elapsed() + 2 * dt < DEADLINE_S:
             n_warm += 1
             continue
         times.append(dt)
         infos.append(info)
-        if spent + dt > budget:
+        if spent + dt > budget or elapsed() + dt > DEADLINE_S:
             break
-    ctx.close()
-    t_solve = float(np.mean(times))
+    if ctx is not None:
+        ctx.close()
+    if extrapolated is not None:
+        # last resort (stated in the line): the complete solve does not fit the step's wall-clock limit
+        t_solve = extrapolated["predicted"]
+        times = []
+
+        class _I:
+            outer_iterations, inner_iterations = extrapolated["n_outer"], 0
+            final_residual, status = float("nan"), -1
+
+        info = _I()
+    else:
+        t_solve = float(np.mean(times))
+        info = infos[-1]
     value = prob.n_dofs / t_solve
-    info = infos[-1]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": len(times), "warmup": n_warm, "requested": {"steps": args.steps, "warmup": args.warmup},
+        "steps": max(1, len(times)), "warmup": n_warm, "requested": {"steps": args.steps, "warmup": args.warmup},
         "ms_per_step": t_solve * 1e3, "higher_is_better": True,
         "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": config_of(wname, w, prob.n_dofs, world, args.scaling),
@@ -218,9 +267,14 @@ def run_reference(args, w, wname):
                   "final_residual": info.final_residual, "status": int(info.status), "setup_s": t_setup,
                   "solve_s_each": times},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{len(times)} COMPLETE outer solve(s) of the benched problem ({prob.n_dofs} DoFs) by the "
-                                   f"oracle port on {cores} OpenMP threads after {n_warm} warm-up solve(s); measured, not "
-                                   f"extrapolated; run bounded by a {budget:.0f} s solve budget"},
+                         "sample": (f"{len(times)} COMPLETE outer solve(s) of the benched problem ({prob.n_dofs} DoFs) by the "
+                                    f"oracle port on {cores} OpenMP threads after {n_warm} warm-up solve(s); measured, not "
+                                    f"extrapolated; run bounded by a {budget:.0f} s solve budget") if extrapolated is None else
+                                   (f"EXTRAPOLATED (the complete solve was predicted at {extrapolated['predicted']:.0f} s and did not "
+                                    f"fit the {DEADLINE_S:.0f} s step limit): first {extrapolated['outer_probe']} outer iterations "
+                                    f"({extrapolated['inner_probe']} inner) of the benched problem took {extrapolated['t_probe']:.1f} s "
+                                    f"on {cores} OpenMP threads, scaled to {extrapolated['n_outer']} outer iterations"),
+                         "extrapolated": extrapolated is not None},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(json.dumps(line))
@@ -362,6 +416,7 @@ def run_ours(args, w, wname):
         lp = part.distribute_problem(prob, H, 0, 1)
         lp.rhs_local, lp.augment_rhs, lp.meta = lp.scatter(prob.rhs), bool(prob.augment_rhs), meta
     t_gen = time.perf_counter() - t0
+    torch.cuda.empty_cache()  # the generators' torch scratch must not sit in the caching allocator beside the library
     log(f"rank {rank}: problem + hierarchy + partition in {t_gen:.1f} s")
     cfg = lp.config
     cfg.device = local_rank
@@ -412,14 +467,28 @@ def run_ours(args, w, wname):
             raise RuntimeError(f"fdal_solve status {st}: {ctx.api.last_error(ctx._h)}")
         return info
 
-    for _ in range(args.warmup):
+    # the first solve also tells how many more fit before the deadline (same decision on every rank)
+    n_warm, n_steps = args.warmup, args.steps
+    t0 = time.perf_counter()
+    first = one_step()
+    t_first = allmax(time.perf_counter() - t0)
+    reserve = 45.0 + (0.6 * (t_gen + t_setup) if (world == 1 and not args.no_parity) else 20.0)
+    fit = int(max(1.0, (DEADLINE_S - allmax(elapsed()) - reserve) / max(t_first, 1e-3)))
+    if fit < n_warm - 1 + n_steps:
+        n_warm = max(1, min(n_warm, fit // 4 + 1))
+        n_steps = max(1, min(n_steps, fit - (n_warm - 1)))
+        log(f"rank {rank}: a solve takes {t_first:.1f} s, {fit} fit before the deadline: {n_warm} warm-up + {n_steps} timed steps "
+            f"instead of {args.warmup} + {args.steps}")
+    for _ in range(max(0, n_warm - 1)):
         one_step()
+    if n_warm == 0:
+        n_warm = 1  # the probing solve above was one
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
     t_region = time.perf_counter()
     infos, walls = [], []
-    for _ in range(args.steps):
+    for _ in range(n_steps):
         t0 = time.perf_counter()
         infos.append(one_step())
         barrier()
@@ -431,7 +500,7 @@ def run_ours(args, w, wname):
     e2e_s = allmax(float(np.mean(walls)))
     x_loc = h_x.numpy().copy()
     last = infos[-1]
-    log(f"rank {rank}: {args.steps} steps, {ms_step:.1f} ms/solve device, {e2e_s*1e3:.1f} ms end to end, "
+    log(f"rank {rank}: {n_steps} steps, {ms_step:.1f} ms/solve device, {e2e_s*1e3:.1f} ms end to end, "
         f"{last.outer_iterations} outer / {last.inner_iterations} inner")
 
     # ---- per-kernel roofline, timed live with CUDA events on the library's stream ------
@@ -462,9 +531,12 @@ def run_ours(args, w, wname):
     if world > 1:
         gathered = [None] * world if rank == 0 else None
         dist.gather_object((x_loc, rhs), gathered, dst=0, group=gloo)
+    skip_oracle = world == 1 and elapsed() + 0.6 * (t_gen + t_setup) > DEADLINE_S
     if rank == 0 and not args.no_parity:
         try:
-            if world == 1:
+            if skip_oracle:
+                parity = {"skipped": f"{elapsed():.0f} s into a {DEADLINE_S:.0f} s step: no time left for the oracle context"}
+            elif world == 1:
                 parity, cpu_sample = oracle_checks(prob, H, ctx, lp, x_loc, rhs, int(last.inner_iterations),
                                                    max(1, os.cpu_count() or 1))
             else:
@@ -492,7 +564,8 @@ def run_ours(args, w, wname):
     if rank == 0:
         res = {
             "metric": METRIC, "value": n_dofs_global / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "steps": n_steps, "warmup": n_warm, "requested": {"steps": args.steps, "warmup": args.warmup},
+            "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_of(wname, w, n_dofs_global, world, args.scaling),
             "solve": {"outer_iterations": int(last.outer_iterations), "inner_iterations": int(last.inner_iterations),

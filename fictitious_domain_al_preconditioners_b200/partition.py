@@ -186,17 +186,22 @@ class LocalHierarchy:
     replicated: bool = False
 
 
-def replicate_from(sizes, nranks: int, max_rows: int | None = None) -> int:
+def replicate_from(nnzs, nranks: int, max_nnz: int | None = None) -> int:
     """First level of the hierarchy that is agglomerated onto every rank: the first one (after the
-    finest) with at most ``max_rows`` rows (env FDAL_REP_ROWS, default 60000); the coarsest level is
-    always replicated.  Below that size a halo exchange costs more than the rows it saves."""
+    finest) whose operator has at most ``max_nnz`` non-zeros (env FDAL_REP_NNZ, default 8e6 = ~100 MB,
+    ~15 us of HBM time per mat-vec; FDAL_REP_ROWS=0 keeps every level but the coarsest partitioned); the
+    coarsest level is always replicated.  Below that size a halo exchange (~20 us of latency) costs more
+    than the redundant rows.  The rule looks at non-zeros, not rows: the coarse operators of the 3-D
+    Q2 problems have few rows but 600-1400 entries per row and must stay partitioned."""
     import os
 
-    if max_rows is None:
-        max_rows = int(os.environ.get("FDAL_REP_ROWS", "60000"))
-    nl = len(sizes)
+    if max_nnz is None:
+        max_nnz = int(float(os.environ.get("FDAL_REP_NNZ", "8e6")))
+        if os.environ.get("FDAL_REP_ROWS") == "0":
+            max_nnz = 0
+    nl = len(nnzs)
     for l in range(1, nl):
-        if sizes[l] <= max_rows:
+        if nnzs[l] <= max_nnz:
             return l
     return nl - 1
 
@@ -300,7 +305,7 @@ class Distributor:
                 self.hier[which] = H  # immersed block: replicated
                 continue
             nl = len(H.levels)
-            rep_from = replicate_from([L.A.shape[0] for L in H.levels], nranks) if nranks > 1 else nl - 1
+            rep_from = replicate_from([L.A.nnz for L in H.levels], nranks) if nranks > 1 else nl - 1
             levels = []
             order_f, off_f = self.order0, self.off0
             rep_off = off_f

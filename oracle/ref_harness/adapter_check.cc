@@ -11,12 +11,15 @@
  *   adapter_solve            fdal_dealii::solve  (replaces solver_fgmres.solve(AA, x, b, P))
  *   adapter_export_csr       fdal_dealii::export_csr from a dealii::SparseMatrix
  *   adapter_to_control       fdal_dealii::to_control
+ *   adapter_export_amg       fdal_dealii::export_amg from a TrilinosWrappers::PreconditionAMG whose ML
+ *                            hierarchy (stand-in types of ref_harness/trilinos_stub, laid out like ML's:
+ *                            Amat[l], Pmat[l+1], Rmat[l], Amat[l].lambda_max) is filled from the caller's levels
  *
  * Built twice by ../Makefile: against the CPU oracle (oracle_shim.h renames fdal_* to fdalo_*)
  * -> _ref/libadapter_oracle.so, and against the CUDA library -> _ref/libadapter_cuda.so.
  * Return codes: 0 ok, 1 SolverControl::NoConvergence was thrown, 2 any other exception.
  */
-#define FDAL_DEALII_NO_TRILINOS
+#define FDAL_STUB_TRILINOS /* export_amg compiles against ref_harness/trilinos_stub (ML / Epetra stand-ins) */
 #include <augmented_lagrangian_preconditioner.h>
 
 #include "fdal_dealii.h"
@@ -144,5 +147,42 @@ void adapter_to_control(int type, unsigned int max_steps, double tol, double red
     *out = fdal_dealii::to_control(dealii::IterationNumberControl(max_steps, tol));
   else
     *out = fdal_dealii::to_control(dealii::SolverControl(max_steps, tol));
+}
+
+/* levels: n_levels operators A_l; P[l] (n_l x n_{l+1}) and R[l] (n_{l+1} x n_l) for l < n_levels - 1, all CSR with
+ * int32 row pointers, concatenated: mats = [A_0, P_0, R_0, A_1, P_1, R_1, ..., A_L] */
+int adapter_export_amg(fdal_ctx *ctx, int which, int n_levels, const int32_t *n_rows, const int32_t *n_cols,
+                       const int32_t *const *rp, const int32_t *const *ci, const double *const *val,
+                       const double *lambda_max, int sweeps, double alpha) {
+  return guarded([&] {
+    std::vector<MlStubCsr> store(3 * n_levels);
+    std::vector<ML_Operator> Amat(n_levels), Pmat(n_levels), Rmat(n_levels);
+    auto fill = [&](int slot, ML_Operator &op) {
+      MlStubCsr &m = store[slot];
+      m.n_rows = n_rows[slot];
+      m.n_cols = n_cols[slot];
+      m.rp.assign(rp[slot], rp[slot] + m.n_rows + 1);
+      m.ci.assign(ci[slot], ci[slot] + m.rp[m.n_rows]);
+      m.v.assign(val[slot], val[slot] + m.rp[m.n_rows]);
+      op.data = &m;
+      op.invec_leng = m.n_cols;
+      op.outvec_leng = m.n_rows;
+    };
+    for (int l = 0; l < n_levels; ++l) {
+      fill(3 * l, Amat[l]);
+      Amat[l].lambda_max = lambda_max[l];
+      if (l + 1 < n_levels) {
+        fill(3 * l + 1, Pmat[l + 1]); /* ML: Pmat[l+1] prolongates level l+1 -> l */
+        fill(3 * l + 2, Rmat[l]);     /* ML: Rmat[l] restricts level l -> l+1 */
+      }
+    }
+    ML ml;
+    ml.ML_num_actual_levels = ml.ML_num_levels = n_levels;
+    ml.Amat = Amat.data();
+    ml.Pmat = Pmat.data();
+    ml.Rmat = Rmat.data();
+    const dealii::TrilinosWrappers::PreconditionAMG amg(std::make_shared<ML_Epetra::MultiLevelPreconditioner>(&ml));
+    fdal_dealii::export_amg(ctx, which, amg, sweeps, alpha);
+  });
 }
 }
