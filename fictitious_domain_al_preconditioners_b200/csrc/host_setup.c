@@ -159,3 +159,36 @@ int fdal_host_get_max_threads(void) {
   return 1;
 #endif
 }
+
+/* ---- row-partition helpers (partition.py; rank-0 setup of the multi-GPU runs) ------------------- */
+/* marks[c] = 1 for every column of indices[0:nnz) outside [c0, c1) (racy stores of the same value) */
+void fdal_host_mark_foreign_cols(int64_t nnz, const int32_t *indices, int64_t c0, int64_t c1, uint8_t *marks) {
+#pragma omp parallel for schedule(static)
+  for (int64_t k = 0; k < nnz; ++k) {
+    const int64_t c = indices[k];
+    if (c < c0 || c >= c1) marks[c] = 1;
+  }
+}
+/* local column numbering [owned | halo]: owned c -> c - c0, foreign c -> n_owned + position of c in the
+ * sorted list halo[0:n_halo) */
+void fdal_host_localize_cols(int64_t nnz, const int32_t *indices, int64_t c0, int64_t c1, const int64_t *halo,
+                             int64_t n_halo, int32_t *out) {
+  const int64_t n_owned = c1 - c0;
+#pragma omp parallel for schedule(static)
+  for (int64_t k = 0; k < nnz; ++k) {
+    const int64_t c = indices[k];
+    if (c >= c0 && c < c1) {
+      out[k] = (int32_t)(c - c0);
+    } else {
+      int64_t lo = 0, hi = n_halo;
+      while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (halo[mid] < c)
+          lo = mid + 1;
+        else
+          hi = mid;
+      }
+      out[k] = (int32_t)(n_owned + lo);
+    }
+  }
+}

@@ -61,27 +61,56 @@ def _node_complete(cols: np.ndarray, bs: int) -> np.ndarray:
 
 
 _NEEDS_CACHE: dict = {}
+_C_PATH_MIN_NNZ = 1_000_000  # row slices with more entries than this are cut by the OpenMP helpers
 
 
 def clear_cache():
     _NEEDS_CACHE.clear()
 
 
+def _host_lib():
+    import ctypes as C
+
+    from .amg_setup import _host
+
+    lib = _host()
+    if not getattr(lib, "_part_ready", False):
+        p64, p32, pu8 = C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_uint8)
+        lib.fdal_host_mark_foreign_cols.restype = None
+        lib.fdal_host_mark_foreign_cols.argtypes = [C.c_int64, p32, C.c_int64, C.c_int64, pu8]
+        lib.fdal_host_localize_cols.restype = None
+        lib.fdal_host_localize_cols.argtypes = [C.c_int64, p32, C.c_int64, C.c_int64, p64, C.c_int64, p32]
+        lib._part_ready = True
+    return lib
+
+
 def _halo_needs(A: sp.csr_matrix, row_off, col_off, col_bs: int):
     """For every rank q: the sorted, node-complete list of columns its rows touch outside its
     own column range.  Cached per matrix object so that cutting all ranks' shares on one
-    process (rank-0 setup) costs one pass instead of one per rank."""
+    process (rank-0 setup) costs one pass instead of one per rank.  The scan over the 10^9 column
+    indices of the fine matrices runs in the OpenMP helper (csrc/host_setup.c)."""
+    import ctypes as C
+
     key = (id(A), A.nnz, tuple(int(x) for x in row_off), tuple(int(x) for x in col_off), col_bs)
     hit = _NEEDS_CACHE.get(key)
     if hit is not None:
         return hit
     nranks = len(row_off) - 1
+    lib = _host_lib() if A.indices.dtype == np.int32 else None
     out = []
     for q in range(nranks):
         lo, hi = int(A.indptr[int(row_off[q])]), int(A.indptr[int(row_off[q + 1])])
-        cq = A.indices[lo:hi].astype(np.int64)
         q0, q1 = int(col_off[q]), int(col_off[q + 1])
-        out.append(_node_complete(cq[(cq < q0) | (cq >= q1)], col_bs))
+        if lib is not None and hi - lo > _C_PATH_MIN_NNZ:
+            marks = np.zeros(A.shape[1], dtype=np.uint8)
+            idx = A.indices[lo:hi]
+            lib.fdal_host_mark_foreign_cols(hi - lo, idx.ctypes.data_as(C.POINTER(C.c_int32)), q0, q1,
+                                            marks.ctypes.data_as(C.POINTER(C.c_uint8)))
+            foreign = np.flatnonzero(marks).astype(np.int64)
+            out.append(_node_complete(foreign, col_bs))
+        else:
+            cq = A.indices[lo:hi].astype(np.int64)
+            out.append(_node_complete(cq[(cq < q0) | (cq >= q1)], col_bs))
     _NEEDS_CACHE[key] = out
     return out
 
@@ -90,21 +119,35 @@ def localize(A: sp.csr_matrix, row_off: np.ndarray, col_off: np.ndarray, rank: i
     """Rows row_off[rank]:row_off[rank+1] of the (renumbered) global matrix with a halo plan
     over the column space partitioned by col_off.  col_bs > 1: the column space is
     node-interleaved with col_bs components per node and halos hold whole nodes."""
+    import ctypes as C
+
     nranks = len(row_off) - 1
     A = A.tocsr()
     if nranks == 1:  # nothing to cut: the whole matrix, empty plan
         z = np.zeros(1, dtype=np.int32)
         return DistCsr(A, HaloPlan(A.shape[1], 0, z, np.empty(0, np.int32), z.copy(), np.empty(0, np.int64)))
     c0, c1 = int(col_off[rank]), int(col_off[rank + 1])
-    sub = A[int(row_off[rank]): int(row_off[rank + 1])].tocsr()
-    cols = sub.indices.astype(np.int64)
-    owned = (cols >= c0) & (cols < c1)
+    r0, r1 = int(row_off[rank]), int(row_off[rank + 1])
     needs = _halo_needs(A, row_off, col_off, col_bs)  # per rank: node-complete non-owned columns
-    halo_globals = needs[rank]
-    newcol = np.empty_like(cols)
-    newcol[owned] = cols[owned] - c0
-    newcol[~owned] = (c1 - c0) + np.searchsorted(halo_globals, cols[~owned])
-    local = sp.csr_matrix((sub.data, newcol.astype(np.int32), sub.indptr), shape=(sub.shape[0], (c1 - c0) + halo_globals.size))
+    halo_globals = np.ascontiguousarray(needs[rank], dtype=np.int64)
+    lo, hi = int(A.indptr[r0]), int(A.indptr[r1])
+    indptr = (A.indptr[r0: r1 + 1] - A.indptr[r0]).astype(np.int64 if hi - lo >= 2**31 - 1 else np.int32)
+    if A.indices.dtype == np.int32 and hi - lo > _C_PATH_MIN_NNZ:
+        # views of the owner's rows (no copy of the values), columns renumbered by the OpenMP helper
+        idx = A.indices[lo:hi]
+        newcol = np.empty(hi - lo, dtype=np.int32)
+        _host_lib().fdal_host_localize_cols(hi - lo, idx.ctypes.data_as(C.POINTER(C.c_int32)), c0, c1,
+                                            halo_globals.ctypes.data_as(C.POINTER(C.c_int64)), halo_globals.size,
+                                            newcol.ctypes.data_as(C.POINTER(C.c_int32)))
+        data = A.data[lo:hi]
+    else:
+        cols = A.indices[lo:hi].astype(np.int64)
+        owned = (cols >= c0) & (cols < c1)
+        newcol = np.empty(cols.size, dtype=np.int32)
+        newcol[owned] = cols[owned] - c0
+        newcol[~owned] = (c1 - c0) + np.searchsorted(halo_globals, cols[~owned])
+        data = A.data[lo:hi]
+    local = sp.csr_matrix((data, newcol, indptr), shape=(r1 - r0, (c1 - c0) + halo_globals.size), copy=False)
     owner = np.searchsorted(col_off, halo_globals, side="right") - 1
     recv_counts = np.bincount(owner, minlength=nranks).astype(np.int32)
     # what every other rank needs from my owned range

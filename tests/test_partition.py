@@ -376,3 +376,21 @@ def test_random_matrices_through_emulated_halo_exchange(seed):
             hg = part.localize(A, row_off, col_off, r, bs).plan.halo_globals
             assert hg.size % bs == 0 and np.array_equal(hg.reshape(-1, bs)[:, 0] % bs, np.zeros(hg.size // bs))
         part.clear_cache()
+
+
+def test_openmp_cut_helpers_match_the_numpy_path(monkeypatch):
+    """localize() cuts the 10^9-entry fine matrices with the OpenMP helpers of csrc/host_setup.c; on the same
+    matrix they must give exactly the numpy path's local matrices and halo plans."""
+    prob = syn.stokes_immersed_boundary(dim=3, nel=6, r_emb=1, numbering="node")
+    A = prob.A.tocsr()
+    off = part.split_offsets(A.shape[0], 4, 3)
+    ref = [part.localize(A, off, off, r, 3) for r in range(4)]
+    part.clear_cache()
+    monkeypatch.setattr(part, "_C_PATH_MIN_NNZ", 0)
+    got = [part.localize(A, off, off, r, 3) for r in range(4)]
+    part.clear_cache()
+    for a, g in zip(ref, got):
+        assert (a.local != g.local).nnz == 0 and a.local.shape == g.local.shape
+        assert np.array_equal(a.local.indices, g.local.indices) and np.array_equal(a.local.indptr, g.local.indptr)
+        for f in ("send_counts", "send_idx", "recv_counts", "halo_globals"):
+            assert np.array_equal(getattr(a.plan, f), getattr(g.plan, f)), f
