@@ -199,34 +199,39 @@ def run_reference(args, w, wname):
     times, infos, spent, n_warm = [], [], 0.0, 0
     want_warm = args.warmup
     extrapolated = None
+    ctx = syn.setup_context(oracle.OracleContext(prob.config, threads=cores), prob, H, oracle=True)
+    rhs = ctx.augment_rhs(prob.rhs) if prob.augment_rhs else prob.rhs
     if prob.n_dofs > int(float(os.environ.get("FDAL_REF_PROBE_MIN_DOFS", "2e6"))):
-        # a complete solve of a problem this size takes minutes: time the first outer iterations to see whether
-        # it fits the step's wall-clock limit (own context, closed again: two oracle copies of the matrices
-        # would not fit the host memory beside the scipy originals)
-        import copy
-
-        cfg2 = copy.deepcopy(prob.config)
-        cfg2.outer.max_steps = 2
-        p2 = copy.copy(prob)
-        p2.config = cfg2
-        pctx = syn.setup_context(oracle.OracleContext(cfg2, threads=cores), p2, H, oracle=True)
-        prhs = pctx.augment_rhs(prob.rhs) if prob.augment_rhs else prob.rhs
+        # a complete solve of a problem this size takes minutes.  Go / no-go against the step's wall-clock limit
+        # from one V-cycle + one augmented apply (the work of one inner PCG iteration) times the inner
+        # iterations such a solve takes (FDAL_EXPECTED_INNER, default 400: the CUDA arm needs 361 on the headline problem)
+        r = np.random.default_rng(0).uniform(-1, 1, prob.sizes[0])
         t0 = time.perf_counter()
-        _, pinfo = pctx.solve(prhs, raise_on_failure=False)
-        t_probe = time.perf_counter() - t0
-        pctx.close()
-        del pctx
-        n_outer_gpu = int(os.environ.get("FDAL_EXPECTED_OUTER", "0")) or 12
-        predicted = t_probe / max(1, pinfo.outer_iterations) * n_outer_gpu
-        log(f"reference arm: probe of {pinfo.outer_iterations} outer iterations took {t_probe:.1f} s; a complete solve is "
-            f"predicted at {predicted:.0f} s, {DEADLINE_S - elapsed():.0f} s left before the deadline")
-        if predicted * 1.25 + 30 > DEADLINE_S - elapsed():
+        ctx.apply_amg(r)
+        ctx.apply_aug(r)
+        t_it = time.perf_counter() - t0
+        n_inner = int(os.environ.get("FDAL_EXPECTED_INNER", "400"))
+        predicted = 1.08 * t_it * n_inner
+        log(f"reference arm: one inner iteration's work takes {t_it:.2f} s; a complete solve is predicted at {predicted:.0f} s, "
+            f"{DEADLINE_S - elapsed():.0f} s left before the deadline")
+        if predicted * 1.15 + 20 > DEADLINE_S - elapsed():
+            # last resort: time the first two outer iterations (own context with max_steps = 2) and extrapolate
+            import copy
+
+            ctx.close()
+            ctx = None
+            cfg2 = copy.deepcopy(prob.config)
+            cfg2.outer.max_steps = 2
+            p2 = copy.copy(prob)
+            p2.config = cfg2
+            pctx = syn.setup_context(oracle.OracleContext(cfg2, threads=cores), p2, H, oracle=True)
+            t0 = time.perf_counter()
+            _, pinfo = pctx.solve(rhs, raise_on_failure=False)
+            t_probe = time.perf_counter() - t0
+            pctx.close()
+            n_outer_gpu = int(os.environ.get("FDAL_EXPECTED_OUTER", "0")) or 12
             extrapolated = dict(t_probe=t_probe, outer_probe=int(pinfo.outer_iterations), inner_probe=int(pinfo.inner_iterations),
-                                n_outer=n_outer_gpu, predicted=predicted)
-    ctx = None
-    if extrapolated is None:
-        ctx = syn.setup_context(oracle.OracleContext(prob.config, threads=cores), prob, H, oracle=True)
-        rhs = ctx.augment_rhs(prob.rhs) if prob.augment_rhs else prob.rhs
+                                n_outer=n_outer_gpu, predicted=t_probe / max(1, pinfo.outer_iterations) * n_outer_gpu)
     while extrapolated is None and len(times) < max(1, args.steps):
         t0 = time.perf_counter()
         _, info = ctx.solve(rhs, raise_on_failure=False)

@@ -3,10 +3,12 @@
  * fdal.h: the reference-side binding a maintainer adds next to
  * augmented_lagrangian_preconditioner.h.  deal.II (>= 9.6), Trilinos ML and UMFPACK are not
  * installed in the build image, so it has never been compiled against the real
- * libraries.  What IS compiled and run here (tests/test_dealii_adapter.py): everything except
- * export_amg (-DFDAL_DEALII_NO_TRILINOS), against the stand-in deal.II types of
- * oracle/ref_harness/dealii_stub, together with the reference's own preconditioner classes —
- * the reference class built from this adapter's LinearOperators reproduces fdal_apply_prec.
+ * libraries.  What IS compiled and run here (tests/test_dealii_adapter.py): all of it, against the
+ * stand-in deal.II types of oracle/ref_harness/dealii_stub and — for export_amg — the ML / Epetra
+ * stand-ins of oracle/ref_harness/trilinos_stub (real type and member names, minimal behaviour),
+ * together with the reference's own preconditioner classes: the reference class built from this
+ * adapter's LinearOperators reproduces fdal_apply_prec, and a context filled by export_amg applies the
+ * same V-cycle as one filled through fdal_amg_set_level.  -DFDAL_DEALII_NO_TRILINOS drops export_amg.
  *
  * What it provides:
  *   fdal_dealii::export_csr          dealii::SparseMatrix<double>            -> fdal_set_csr
@@ -311,8 +313,10 @@ inline void solve(fdal_ctx *ctx, dealii::BlockVector<double> &x, const dealii::B
   fdal_solve_info info;
   const int st = fdal_solve(ctx, b.data(), sol.data(), &info);
   if (info_out) *info_out = info;
-  if (st == FDAL_ERR_OUTER_NO_CONVERGENCE || st == FDAL_ERR_INNER_NO_CONVERGENCE || st == FDAL_ERR_MASS_NO_CONVERGENCE)
+  if (st == FDAL_ERR_OUTER_NO_CONVERGENCE || st == FDAL_ERR_INNER_NO_CONVERGENCE || st == FDAL_ERR_MASS_NO_CONVERGENCE) {
+    internal::scatter(sol, x); /* deal.II leaves the last iterate in x when it throws */
     throw dealii::SolverControl::NoConvergence(info.outer_iterations, info.final_residual);
+  }
   check(ctx, st);
   internal::scatter(sol, x);
 }

@@ -53,6 +53,10 @@ def load(flavour: str):
         lib.adapter_export_csr.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, pi64, C.POINTER(C.c_int32), pd]
         lib.adapter_to_control.argtypes = [C.c_int, C.c_uint, C.c_double, C.c_double, C.POINTER(b.Control)]
         lib.adapter_to_control.restype = None
+        pp32, ppd = C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.POINTER(C.c_double))
+        lib.adapter_export_amg.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), pp32,
+                                           pp32, ppd, pd, C.c_int, C.c_double]
+        lib.adapter_export_amg.restype = C.c_int
         for f in ("adapter_reference_vmult", "adapter_al_vmult", "adapter_solve", "adapter_export_csr"):
             getattr(lib, f).restype = C.c_int
         _libs[flavour] = lib
@@ -102,3 +106,38 @@ def to_control(lib, type_, max_steps, tol, reduce=0.0):
     out = b.Control()
     lib.adapter_to_control(type_, max_steps, tol, reduce, C.byref(out))
     return out
+
+
+def export_amg(lib, ctx, which, hierarchy):
+    """fdal_dealii::export_amg from a TrilinosWrappers::PreconditionAMG stand-in whose ML hierarchy
+    (ref_harness/trilinos_stub: Amat[l], Pmat[l+1], Rmat[l], Amat[l].lambda_max) is filled from `hierarchy`."""
+    import scipy.sparse as sp
+
+    levels = hierarchy.levels
+    nl = len(levels)
+    mats = []
+    for l, L in enumerate(levels):
+        mats.append(sp.csr_matrix(L.A))
+        if l + 1 < nl:
+            mats.append(sp.csr_matrix(L.P))
+            mats.append(sp.csr_matrix(L.R if L.R is not None else L.P.T))
+        else:
+            mats += [None, None]
+    keep, rp, ci, val = [], [], [], []
+    n_rows = (C.c_int32 * (3 * nl))()
+    n_cols = (C.c_int32 * (3 * nl))()
+    for k, M in enumerate(mats):
+        if M is None:
+            a = (np.zeros(1, np.int32), np.zeros(1, np.int32), np.zeros(1))
+        else:
+            a = (np.ascontiguousarray(M.indptr, np.int32), np.ascontiguousarray(M.indices, np.int32),
+                 np.ascontiguousarray(M.data, np.float64))
+            n_rows[k], n_cols[k] = M.shape
+        keep.append(a)
+        rp.append(a[0].ctypes.data_as(C.POINTER(C.c_int32)))
+        ci.append(a[1].ctypes.data_as(C.POINTER(C.c_int32)))
+        val.append(a[2].ctypes.data_as(C.POINTER(C.c_double)))
+    lam = np.array([L.lambda_max for L in levels], dtype=np.float64)
+    return lib.adapter_export_amg(ctx._h, which, nl, n_rows, n_cols, (C.POINTER(C.c_int32) * len(rp))(*rp),
+                                  (C.POINTER(C.c_int32) * len(ci))(*ci), (C.POINTER(C.c_double) * len(val))(*val),
+                                  b.dptr(lam), int(hierarchy.cheb_degree), float(hierarchy.eig_ratio))

@@ -103,3 +103,30 @@ def test_to_control_maps_the_solver_control_family():
     assert (c.type, c.max_steps, c.tol, c.reduce) == (b.CONTROL_REDUCTION, 1000, 1e-12, 1e-9)
     c = ac.to_control(lib, b.CONTROL_ITERATION_NUMBER, 7, 1e-20)
     assert (c.type, c.max_steps) == (b.CONTROL_ITERATION_NUMBER, 7)
+
+
+@pytest.mark.parametrize("name", ["laplace_diag", "stokes2d_diag", "elliptic_modified"])
+def test_export_amg_through_the_ml_standins(name, oracle_mod):
+    """fdal_dealii::export_amg (ML_Epetra::MultiLevelPreconditioner::GetML -> Amat/Pmat/Rmat ->
+    ML_Operator2EpetraCrsMatrix -> ExtractMyRowView -> fdal_amg_set_level) compiled against the ML / Epetra
+    stand-ins of oracle/ref_harness/trilinos_stub and run on a hierarchy laid out the way ML lays it out:
+    the context it fills applies the same V-cycle, bit for bit, as one filled through fdal_amg_set_level."""
+    lib = ac.load("oracle")
+    prob, H = P.get(name)
+    ref = syn.setup_context(oracle_mod.OracleContext(prob.config), prob, H, oracle=True)
+    ctx = oracle_mod.OracleContext(prob.config)
+    for mid, A in ((b.MAT_A, prob.A), (b.MAT_A2, prob.A2), (b.MAT_CT, prob.Ct), (b.MAT_BT, prob.Bt), (b.MAT_MP, prob.Mp),
+                   (b.MAT_M, prob.M)):
+        if A is not None:
+            ctx.set_csr(mid, A)
+    if prob.winv_diag is not None:
+        ctx.set_diag(b.DIAG_W_INV, prob.winv_diag)
+    if prob.config.winv_mode != b.WINV_DIAG:
+        ctx.set_lu(0, prob.M)
+    for which, Hh in H.items():
+        assert ac.export_amg(lib, ctx, which, Hh) == 0
+    ctx.finalize()
+    r = P.rand(prob.sizes[0], 7)
+    assert np.array_equal(ctx.apply_amg(r), ref.apply_amg(r))
+    u = P.rand(prob.n_dofs, 10)
+    assert np.array_equal(ctx.apply_prec(u)[0], ref.apply_prec(u)[0])
