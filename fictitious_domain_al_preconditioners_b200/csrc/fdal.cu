@@ -605,8 +605,8 @@ static void halo_exchange(fdal_ctx *c, const DevCsr &A, const double *x) {
   ncclResult_t r = n->GroupEnd();
   if (r != ncclSuccess && !c->fail) c->fail = FDAL_ERR_NCCL;
 }
-// `grid`: CTAs of the launch.  In peer-channel mode the first g_int CTAs share the interior chunks,
-// the rest acquire the halo and share the boundary chunks (kernels.cuh: chunk_range)
+// `grid`: CTAs of the launch.  In peer-channel mode the first g_bnd CTAs acquire the halo and share the
+// boundary chunks, the rest share the interior chunks (kernels.cuh: chunk_range)
 static inline XVec xv(const fdal_ctx *c, const DevCsr &A, const double *x, int *grid) {
   XVec X{x, A.halo_buf, A.n_owned};
   if (c->p2p && A.chan >= 0 && !c->chans[(size_t)A.chan].nb.empty()) {
@@ -614,9 +614,23 @@ static inline XVec xv(const fdal_ctx *c, const DevCsr &A, const double *x, int *
     X.order = A.order;
     X.n_interior = A.n_interior;
     const int n_bnd = A.n_chunks - A.n_interior;
-    const int g_bnd = n_bnd > 0 ? std::max(1, std::min(n_bnd, std::max(*grid / 8, c->sms))) : 0;
-    X.g_int = A.n_interior > 0 ? std::max(1, std::min(A.n_interior, *grid)) : 0;
-    *grid = std::max(1, X.g_int + g_bnd);
+    const int g = std::max(1, std::min(*grid, A.n_chunks));
+    // Default: every CTA acquires the halo before its loop and all CTAs share all chunks.  The interior /
+    // boundary CTA split (FDAL_SPLIT=1: boundary CTAs acquire, interior CTAs start at once) was measured
+    // and lost: 3-D nel=40 on 2 B200s, V-cycle 2382 us with the split, 1896 us without (profiles/r2_multi_gpu.md)
+    // — the ranks run in lockstep, the flags are there when the kernel starts, and two CTA populations
+    // with different work per chunk finish at different times.
+    static const bool split = getenv("FDAL_SPLIT") != nullptr && atoi(getenv("FDAL_SPLIT")) > 0;
+    if (!split) {
+      X.n_interior = 0;
+      X.g_bnd = g;
+    } else if (n_bnd == 0)
+      X.g_bnd = 0;
+    else if (A.n_interior == 0 || g < 2)
+      X.g_bnd = g;
+    else  // CTAs in proportion to the chunks of each kind, at least one each
+      X.g_bnd = std::max(1, std::min(g - 1, (int)((double)g * n_bnd / A.n_chunks + 0.5)));
+    *grid = g;
   }
   return X;
 }

@@ -86,16 +86,19 @@ struct XVec {
   const double *x;
   const double *halo;
   int n_owned;
-  // multi-GPU with peer channels: halo = ch->recv + (epoch & 1) * cap.  The row chunks are walked in
-  // `order` (the n_interior chunks without halo columns first).  The first g_int CTAs of the grid share
-  // the interior chunks and never wait; the remaining CTAs acquire the halo once, before their loop, and
-  // share the boundary chunks — the peers' pushes overlap the interior rows and no barrier sits inside
-  // the row loop (a barrier there stops ptxas from unrolling the row walk: -13 % on the 3-D V-cycle).
+  // multi-GPU with peer channels: halo = ch->recv + (epoch & 1) * cap.  The row chunks are listed in
+  // `order` (the n_interior chunks without halo columns first).  The grid is split in proportion to the
+  // work: the first g_bnd CTAs acquire the halo once, before their loop, and share the boundary chunks;
+  // the other CTAs share the interior chunks and never wait, so the peers' pushes overlap the interior
+  // rows.  The boundary CTAs come FIRST in block order: a grid larger than what is resident starts its
+  // last blocks only when earlier ones retire, and boundary blocks started last would run alone at the
+  // tail (3-D slabs: 16 % of the rows touch the halo).  No barrier sits inside the row loop (a barrier
+  // there stops ptxas from unrolling the row walk: -13 % on the 3-D V-cycle).
   // ch == nullptr: single GPU or NCCL-filled halo buffer.
   const ChanDev *ch = nullptr;
   const int *order = nullptr;
   int n_interior = 0;
-  int g_int = 0;
+  int g_bnd = 0;
 };
 // ONE load instruction for owned and halo entries (a select on the address, no branch), through the
 // read-only path like every other operand of the row walk.  The halo slot is filled by the peers
@@ -115,9 +118,9 @@ __device__ __forceinline__ ChunkRange chunk_range(XVec &X, int nchunks) {
   if (!DIST) return ChunkRange{(int)blockIdx.x, nchunks, (int)gridDim.x};
   const unsigned long long e = *X.ch->epoch;  // written by the push kernel that precedes this kernel in stream order
   X.halo = X.ch->recv + (size_t)(e & 1ull) * X.ch->cap;
-  if ((int)blockIdx.x < X.g_int) return ChunkRange{(int)blockIdx.x, X.n_interior, X.g_int};
+  if ((int)blockIdx.x >= X.g_bnd) return ChunkRange{(int)blockIdx.x - X.g_bnd, X.n_interior, (int)gridDim.x - X.g_bnd};
   chan_wait(*X.ch, e);
-  return ChunkRange{X.n_interior + ((int)blockIdx.x - X.g_int), nchunks, (int)gridDim.x - X.g_int};
+  return ChunkRange{X.n_interior + (int)blockIdx.x, nchunks, X.g_bnd};
 }
 template <bool DIST>
 __device__ __forceinline__ int chunk_at(const XVec &X, int p) {

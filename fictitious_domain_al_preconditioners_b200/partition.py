@@ -231,17 +231,21 @@ class LocalHierarchy:
 
 def replicate_from(nnzs, nranks: int, max_nnz: int | None = None) -> int:
     """First level of the hierarchy that is agglomerated onto every rank: the first one (after the
-    finest) whose operator has at most ``max_nnz`` non-zeros (env FDAL_REP_NNZ, default 8e6 = ~100 MB,
-    ~15 us of HBM time per mat-vec; FDAL_REP_ROWS=0 keeps every level but the coarsest partitioned); the
-    coarsest level is always replicated.  Below that size a halo exchange (~20 us of latency) costs more
-    than the redundant rows.  The rule looks at non-zeros, not rows: the coarse operators of the 3-D
-    Q2 problems have few rows but 600-1400 entries per row and must stay partitioned."""
+    finest) whose operator has at most ``max_nnz`` non-zeros; the coarsest level is always replicated.
+    Rule: a partitioned mat-vec costs t/N + ~45 us (push kernel, launch, waiting for the slowest
+    neighbour; measured on 2 and 4 B200s), a replicated one t = 12 B * nnz / ~5 TB/s, so replication
+    wins while nnz <= 1.9e7 / (1 - 1/N) (env FDAL_REP_NNZ overrides; FDAL_REP_ROWS=0 keeps every level
+    but the coarsest partitioned).  The rule looks at non-zeros, not rows: the coarse operators of the
+    3-D Q2 problems have few rows but 600-1400 entries per row."""
     import os
 
     if max_nnz is None:
-        max_nnz = int(float(os.environ.get("FDAL_REP_NNZ", "8e6")))
         if os.environ.get("FDAL_REP_ROWS") == "0":
             max_nnz = 0
+        elif os.environ.get("FDAL_REP_NNZ"):
+            max_nnz = int(float(os.environ["FDAL_REP_NNZ"]))
+        else:
+            max_nnz = int(1.9e7 / (1.0 - 1.0 / max(2, nranks)))
     nl = len(nnzs)
     for l in range(1, nl):
         if nnzs[l] <= max_nnz:

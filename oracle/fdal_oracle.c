@@ -741,14 +741,41 @@ static int fgmres(fdalo_ctx *c, const double *b, double *x, fdal_solve_info *inf
       if (c->fail) break;
       double *w = V[j + 1];
       apply_system(c, Z[j], w);
-      /* classical Gram-Schmidt with one re-orthogonalisation pass (batched
-       * dots); equals deal.II's delayed-CGS Arnoldi basis in exact arithmetic */
+      /* Orthogonalisation.  Default: MODIFIED Gram-Schmidt with deal.II's re-orthogonalisation rule
+       * (LinearAlgebra::OrthogonalizationStrategy::modified_gram_schmidt: project out the basis
+       * vectors one after the other; a second sweep only if the vector lost more than a factor
+       * 10 sqrt(eps) of its length) — deliberately NOT the batched classical Gram-Schmidt with an
+       * unconditional second pass that the CUDA library runs (csrc/fdal.cu: fgmres), so that the two
+       * sides of every parity test orthogonalise with different algorithms; any numerically
+       * orthonormal Arnoldi basis (deal.II >= 9.5 defaults to delayed classical Gram-Schmidt) gives
+       * the same Hessenberg matrix to rounding.  FDALO_ORTHO=cgs2 selects the CUDA library's variant. */
       double *h = H + (int64_t)j * (mb + 1);
-      for (int i = 0; i <= j; ++i) h[i] = vdot(N, w, V[i]);
-      for (int i = 0; i <= j; ++i) vaxpy(N, -h[i], V[i], w);
-      for (int i = 0; i <= j; ++i) h2[i] = vdot(N, w, V[i]);
-      for (int i = 0; i <= j; ++i) vaxpy(N, -h2[i], V[i], w);
-      for (int i = 0; i <= j; ++i) h[i] += h2[i];
+      static int ortho_mode = -1;
+      if (ortho_mode < 0) {
+        const char *e = getenv("FDALO_ORTHO");
+        ortho_mode = (e && strcmp(e, "cgs2") == 0) ? 1 : 0;
+      }
+      if (ortho_mode == 1) {
+        for (int i = 0; i <= j; ++i) h[i] = vdot(N, w, V[i]);
+        for (int i = 0; i <= j; ++i) vaxpy(N, -h[i], V[i], w);
+        for (int i = 0; i <= j; ++i) h2[i] = vdot(N, w, V[i]);
+        for (int i = 0; i <= j; ++i) vaxpy(N, -h2[i], V[i], w);
+        for (int i = 0; i <= j; ++i) h[i] += h2[i];
+      } else {
+        const double norm_start = sqrt(vdot(N, w, w));
+        for (int i = 0; i <= j; ++i) {
+          h[i] = vdot(N, w, V[i]);
+          vaxpy(N, -h[i], V[i], w);
+        }
+        const double norm_after = sqrt(vdot(N, w, w));
+        if (norm_after <= 10.0 * norm_start * sqrt(2.220446049250313e-16)) {
+          for (int i = 0; i <= j; ++i) {
+            const double t = vdot(N, w, V[i]);
+            h[i] += t;
+            vaxpy(N, -t, V[i], w);
+          }
+        }
+      }
       const double hn = sqrt(vdot(N, w, w));
       h[j + 1] = hn;
       if (hn != 0.0) vscale(N, 1.0 / hn, w);

@@ -5,10 +5,13 @@ import os
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-src = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "parity_log.jsonl")
-dst = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "profiles", "r2_parity_table.md")
+import glob
+
+srcs = sys.argv[1:] or sorted(glob.glob(os.path.join(ROOT, "profiles", "r2_parity_log_*.jsonl")) +
+                              glob.glob(os.path.join(ROOT, "gpurun_out", "parity_log*.jsonl")))
+dst = os.path.join(ROOT, "profiles", "r2_parity_table.md")
 rows, multi = {}, {}
-for line in open(src):
+for line in (l for src in srcs for l in open(src)):
     d = json.loads(line)
     if "what" in d and "err" in d:
         rows[(d["test"], d["what"])] = d  # the last run of an assertion wins
@@ -16,7 +19,7 @@ for line in open(src):
         multi[d["test"]] = d
 out = ["# Parity evidence (round 2)", "",
        "Every parity assertion of the `-m gpu` suites, as measured on a B200 by the run that produced",
-       "`gpurun_out/parity_log.jsonl` (`scripts/parity_table.py`).  `err` = relative 2-norm error of the CUDA",
+       "`profiles/r2_parity_log_*.jsonl` (`scripts/parity_table.py`; raw logs tracked beside this table).  `err` = relative 2-norm error of the CUDA",
        "result against the CPU oracle (or the named golden vector); `tol` = the tolerance the assertion applied",
        "(1e-12 for operator / V-cycle / W^-1 applications; for CG-based applications `max(1e-12, 50 x the",
        "oracle's own sensitivity to a one-ulp input perturbation)`, see tests/test_gpu_parity.py).", "",

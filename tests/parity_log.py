@@ -3,9 +3,11 @@ tolerance, iteration counts) to gpurun_out/parity_log.jsonl; scripts/parity_tabl
 a GPU run into profiles/r2_parity_table.md (tracked)."""
 import json
 import os
+import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LOG = os.path.join(ROOT, "gpurun_out", "parity_log.jsonl")
+# one file per run (gpurun merges gpurun_out/ back file by file: a fixed name would be overwritten by the next call)
+LOG = os.path.join(ROOT, "gpurun_out", f"parity_log_{os.environ.get('FDAL_PARITY_TAG') or time.strftime('%m%d_%H%M')}.jsonl")
 
 
 def _plain(v):

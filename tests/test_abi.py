@@ -89,3 +89,15 @@ def test_header_is_plain_c_and_a_c_client_links(tmp_path):
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.startswith("fdal ")
+
+
+def test_dealii_example_compiles():
+    """examples/dealii_immersed_laplace_solve.cc — the function a maintainer adds to immersed_laplace.cc —
+    goes through a C++17 compiler against the stand-in deal.II / Trilinos-ML types (export_amg included)."""
+    import subprocess
+
+    stub = os.path.join(ROOT, "oracle", "ref_harness")
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Wextra", "-Werror",
+                    "-I", os.path.join(stub, "dealii_stub"), "-I", os.path.join(stub, "trilinos_stub"),
+                    "-I", os.path.join(ROOT, "include"), "-DFDAL_STUB_TRILINOS",
+                    os.path.join(ROOT, "examples", "dealii_immersed_laplace_solve.cc")], check=True)
