@@ -14,7 +14,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB = os.path.join(CSRC, "libfdal.so")
-SOURCES = ["fdal.cu"]
+SOURCES = ["fdal.cu", "setup.cu"]
 HEADERS = ["kernels.cuh", os.path.join("..", "..", "include", "fdal.h")]
 
 

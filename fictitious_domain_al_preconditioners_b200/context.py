@@ -321,3 +321,32 @@ class ALContext:
             )
         )
         return ms.value, by.value, nl.value
+
+
+def assemble_al_term(A, point_dofs, point_phi, weight, device: int = 0, api: b.Api | None = None):
+    """``A + sum_q weight[q] phi_q phi_q^T`` on the device (``fdal_assemble_al_term``): the
+    operator-form AL term of immersed_laplace.cc:659-702 scattered into the CSR values of ``A`` (scipy CSR;
+    its pattern must already hold the couplings).  ``point_dofs`` / ``point_phi``: (n_points, dofs_per_cell)
+    dof indices (negative = skip) and shape-function values of the background cell of every immersed
+    quadrature point; ``weight``: gamma * JxW.  Returns a new scipy CSR matrix with the same pattern."""
+    import scipy.sparse as sp
+
+    if api is None:
+        from .lib import load
+
+        api = load()
+    A = sp.csr_matrix(A)
+    rp = np.ascontiguousarray(A.indptr, dtype=np.int64)
+    ci = np.ascontiguousarray(A.indices, dtype=np.int32)
+    v = np.array(A.data, dtype=np.float64, copy=True)
+    dofs = np.ascontiguousarray(point_dofs, dtype=np.int32)
+    phi = np.ascontiguousarray(point_phi, dtype=np.float64)
+    w = np.ascontiguousarray(weight, dtype=np.float64)
+    assert dofs.shape == phi.shape and dofs.ndim == 2 and w.size == dofs.shape[0]
+    missing = C.c_int64(0)
+    st = api.assemble_al_term(device, A.shape[0], rp.ctypes.data_as(C.POINTER(C.c_int64)),
+                              ci.ctypes.data_as(C.POINTER(C.c_int32)), b.dptr(v), dofs.shape[0], dofs.shape[1],
+                              dofs.ctypes.data_as(C.POINTER(C.c_int32)), b.dptr(phi), b.dptr(w), C.byref(missing))
+    if st != b.OK:
+        raise FdalError(st, f"fdal_assemble_al_term failed ({missing.value} entries missing from the sparsity pattern)")
+    return sp.csr_matrix((v, A.indices.copy(), A.indptr.copy()), shape=A.shape)

@@ -306,6 +306,20 @@ int fdal_amg_set_coarse_range(fdal_ctx *ctx, int which, int64_t lo, int64_t hi);
  * library's own kernels (fused into the reductions' last block / the SpMV's boundary chunks) */
 int fdal_comm_mode(const fdal_ctx *ctx);
 
+/* ---- setup phase on the device -----------------------------------
+ * Operator-form AL term (immersed_laplace.cc:659-702 with the particles of utilities.h:755-837;
+ * nitsche_bcs.cc:517-572):  A += sum_q weight[q] * phi_q phi_q^T  scattered into the CSR values of the
+ * stiffness matrix on the device.  The host (deal.II Particles / FEValues) supplies, per immersed
+ * quadrature point q, the dofs_per_cell dof indices of the background cell it lies in (point_dofs, a
+ * negative index skips that local dof) and the shape-function values there (point_phi);
+ * weight[q] = gamma * JxW_q.  val_inout is updated in place (row_ptr / col unchanged; rows need not be
+ * sorted).  Returns FDAL_ERR_SHAPE, with the count in *n_missing_out, if the sparsity pattern lacks an
+ * entry a point needs.  Stand-alone: no fdal_ctx involved. */
+int fdal_assemble_al_term(int device, int64_t n_rows, const int64_t *row_ptr, const int32_t *col,
+                          double *val_inout, int64_t n_points, int32_t dofs_per_cell,
+                          const int32_t *point_dofs, const double *point_phi, const double *weight,
+                          int64_t *n_missing_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -89,3 +89,26 @@ def test_hierarchy_is_galerkin_and_coarsens():
         assert len(set(comp[members])) == 1
     # Dirichlet rows have no strong connection: left out of the coarse grid
     assert np.all(agg[np.diff(H.levels[0].A.indptr) == 1] == -1)
+
+
+def test_add_low_rank_rows_equals_the_general_sparse_add():
+    """The explicit augmented matrix A + gamma Ct W^-1 C is formed by touching only the rows next to the immersed
+    body (synthetic.add_low_rank_rows): bit-identical to scipy's general add + canonicalisation."""
+    import scipy.sparse as sp
+
+    rng = np.random.default_rng(5)
+    A = sp.random(400, 400, density=0.03, random_state=7, format="csr") + sp.identity(400, format="csr")
+    A = syn._csr(A)
+    S = sp.lil_matrix((400, 400))
+    for r in (0, 17, 18, 19, 250, 399):
+        cols = rng.choice(400, 9, replace=False)
+        S[r, cols] = rng.uniform(-1, 1, 9)
+    S = sp.csr_matrix(S)
+    ref = syn._csr(A + S)
+    got = syn.add_low_rank_rows(A, S)
+    assert np.array_equal(got.indptr, ref.indptr) and np.array_equal(got.indices, ref.indices)
+    assert np.array_equal(got.data, ref.data)
+    # nothing to add / an S touching most rows fall back to the general path
+    assert (syn.add_low_rank_rows(A, sp.csr_matrix((400, 400))) != A).nnz == 0
+    dense_S = sp.random(400, 400, density=0.02, random_state=3, format="csr")
+    assert (syn.add_low_rank_rows(A, dense_S) != syn._csr(A + dense_S)).nnz == 0
