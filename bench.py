@@ -112,6 +112,19 @@ def build_problem(w):
     return prob, H
 
 
+def mass_forms(ctx):
+    """How the exact mass inverses (W^-1 = M^-1 / M^-2, Mp^-1) are applied on the device (fdal_mass_solver_info)."""
+    out = {}
+    for which, name in ((0, "M"), (1, "Mp")):
+        try:
+            d = ctx.mass_solver_info(which)
+            if d["form"] != "none":
+                out[name] = d
+        except Exception:
+            pass
+    return out
+
+
 def config_of(wname, w, n_dofs, world, scaling):
     """The keys BOTH arms print (identical for the same job)."""
     return {"workload": wname, "description": w["label"], "n_dofs": int(n_dofs), "n_gpus_job": int(world),
@@ -583,6 +596,7 @@ def run_ours(args, w, wname):
                       "setup_s": {"generate+amg_host": t_gen, "upload+finalize": t_setup},
                       "timed_region_wall_s": wall_total, "graphs": bool(cfg.use_graphs),
                       "block_size": int(cfg.block_size),
+                      "exact_mass_inverses": mass_forms(ctx),
                       "setup": "rank 0 builds and cuts the problem; shares via /dev/shm" if world > 1 else "in process"},
             "e2e": {"value": n_dofs_global / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 16 * N, "d2h_bytes_per_step": 8 * N,
                     "ms_per_step": e2e_s * 1e3,

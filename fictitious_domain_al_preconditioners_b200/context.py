@@ -123,6 +123,10 @@ class ALContext:
         except Exception:
             pass
 
+    def last_error(self) -> str:
+        msg = self.api.last_error(self._h)
+        return msg.decode() if msg else ""
+
     def _check(self, st: int):
         if st == b.OK:
             return
@@ -321,6 +325,18 @@ class ALContext:
             )
         )
         return ms.value, by.value, nl.value
+
+    MASS_FORMS = {0: "none", 1: "pcg_kernels", 2: "pcg_one_cta", 3: "dense", 4: "cheb_kernels", 5: "cheb_persistent"}
+
+    def mass_solver_info(self, which: int = 0) -> dict:
+        """How the exact inverse of the multiplier (which=0) / pressure (which=1) mass matrix is applied
+        (``fdal_mass_solver_info``; CUDA library only)."""
+        form, its = C.c_int32(), C.c_int32()
+        lo, hi, res = C.c_double(), C.c_double(), C.c_double()
+        self._check(self.api.mass_solver_info(self._h, which, C.byref(form), C.byref(its), C.byref(lo), C.byref(hi),
+                                              C.byref(res)))
+        return dict(form=self.MASS_FORMS.get(form.value, str(form.value)), iterations=its.value,
+                    interval=(lo.value, hi.value), verified_residual=res.value)
 
 
 def assemble_al_term(A, point_dofs, point_phi, weight, device: int = 0, api: b.Api | None = None):

@@ -205,6 +205,25 @@ struct CgWs {
   bool graph_ok = true;
 };
 
+// Exact mass solve as a fixed-count Chebyshev iteration on D^-1 M (no inner products).
+//   mode 1: one fused SpMV kernel per iteration (k_spmv<.., EpiCheb>), replayed as a CUDA graph
+//   mode 2: the whole solve in one persistent kernel with the matrix slice of every CTA staged in
+//           shared memory and one grid barrier per iteration (k_mass_cheb_grid)
+struct MassCheb {
+  int mode = 0;
+  int its = 0;
+  double lo = 0.0, hi = 0.0;   // spectral interval of D^-1 M used for the coefficients
+  double verified_resid = 0.0; // |b - M x| / |b| of the calibration right-hand side
+  std::vector<double> coef;    // c1_k, c2_k
+  double *d_coef = nullptr, *xbuf = nullptr;
+  unsigned int *bar = nullptr;
+  int grid = 0, rpc = 0, nnz_cap = 0;
+  size_t smem = 0;
+  cudaGraphExec_t exec = nullptr;  // mode 1: the whole solve (w.bin -> w.z)
+  int64_t exec_nodes = 0;
+  bool graph_ok = true;
+};
+
 }  // namespace fdal
 
 using namespace fdal;
@@ -243,6 +262,7 @@ struct fdal_ctx {
   double *mass_cta_ws = nullptr;       // 5*m scratch of k_mass_pcg_cta (m <= kMassCtaMaxRows)
   double *d_winv_dense = nullptr;      // m x m exact W^-1 (opt-in FDAL_DENSE_WINV=1, m <= kDenseWinvMaxRows)
   int mass_its_m = 0, mass_its_p = 0;  // calibrated fixed iteration counts (exact mass solves)
+  MassCheb mcheb_m, mcheb_p;           // Chebyshev form of the same solves (mode 0: keep the Jacobi-PCG)
   // counters
   int its_a11 = 0, its_a22 = 0, its_mass = 0, n_inner_solves = 0;
   int64_t launches = 0, graph_launches = 0;
@@ -1031,7 +1051,11 @@ static void mass_solve_fixed(fdal_ctx *c, CgWs &w, const DevCsr &M, const double
   if (!done) whole();
   dcopy(c, w.n, w.x, x);
 }
-static int mass_calibrate(fdal_ctx *c, CgWs &w, const DevCsr &M, const double *invdiag, int *its_out) {
+struct CgHistory {
+  std::vector<double> rho, pv;  // r.z and p.Ap of every iteration
+};
+static int mass_calibrate(fdal_ctx *c, CgWs &w, const DevCsr &M, const double *invdiag, int *its_out,
+                          CgHistory *lanczos = nullptr) {
   // count the iterations Jacobi-PCG needs to push the recursive residual below
   // 1e-17 |b| on a rough right-hand side; the solve then always runs that many + 3
   const int64_t n = w.n;
@@ -1053,16 +1077,231 @@ static int mass_calibrate(fdal_ctx *c, CgWs &w, const DevCsr &M, const double *i
   const int cap = c->cfg.exact_mass_max_its > 0 ? c->cfg.exact_mass_max_its : 300;
   int it = 0;
   double rr = rr0;
+  std::vector<double> rho_k, pv_k;  // CG coefficients -> Lanczos matrix of D^-1 M (bounds for the Chebyshev form)
   while (it < cap && std::sqrt(std::fabs(rr)) > 1e-17 * std::sqrt(rr0)) {
     cg_body(c, w, op, pr, x);
     ++it;
-    if ((st = read_scalars(c, w.scal + S_RR, 1, &rr))) return st;
+    double sc[4];
+    if ((st = read_scalars(c, w.scal, 4, sc))) return st;
+    rr = sc[S_RR];
+    rho_k.push_back(sc[S_RHO]);
+    pv_k.push_back(sc[S_PV]);
   }
   *its_out = std::min(cap, it + 3);
+  if (lanczos) {
+    lanczos->rho = rho_k;
+    lanczos->pv = pv_k;
+  }
   if (it >= cap && std::sqrt(std::fabs(rr)) > 1e-17 * std::sqrt(rr0))
     set_err(c, "warning: the exact mass solve stopped at its cap of %d Jacobi-PCG iterations with relative residual %.2e",
             cap, std::sqrt(std::fabs(rr) / rr0));
   return FDAL_OK;
+}
+
+// ---- Chebyshev form of the exact mass solves ----------------------------------------------------
+// extreme eigenvalues of the symmetric tridiagonal matrix (d, e) by Sturm bisection
+static void tridiag_extremes(const std::vector<double> &d, const std::vector<double> &e, double *lo_out, double *hi_out) {
+  const int n = (int)d.size();
+  double gl = d[0], gu = d[0];
+  for (int i = 0; i < n; ++i) {
+    const double r = (i > 0 ? std::fabs(e[(size_t)i - 1]) : 0.0) + (i + 1 < n ? std::fabs(e[(size_t)i]) : 0.0);
+    gl = std::min(gl, d[(size_t)i] - r);
+    gu = std::max(gu, d[(size_t)i] + r);
+  }
+  auto count_below = [&](double x) {  // eigenvalues < x
+    int cnt = 0;
+    double q = d[0] - x;
+    for (int i = 0;; ++i) {
+      if (q < 0.0) ++cnt;
+      if (i + 1 == n) break;
+      if (q == 0.0) q = 1e-300;
+      q = d[(size_t)i + 1] - x - e[(size_t)i] * e[(size_t)i] / q;
+    }
+    return cnt;
+  };
+  auto kth = [&](int k) {  // smallest x with count_below(x) >= k, i.e. the k-th eigenvalue (1-based)
+    double a = gl, b = gu;
+    for (int i = 0; i < 200 && b - a > 1e-15 * std::max(std::fabs(a), std::fabs(b)); ++i) {
+      const double mid = 0.5 * (a + b);
+      if (count_below(mid) >= k)
+        b = mid;
+      else
+        a = mid;
+    }
+    return 0.5 * (a + b);
+  };
+  *lo_out = kth(1);
+  *hi_out = kth(n);
+}
+// Ritz values of D^-1 M from the CG coefficients of the calibration solve (Lanczos connection:
+// T_jj = 1/alpha_j + beta_j/alpha_{j-1}, T_{j,j+1} = sqrt(beta_{j+1})/alpha_j)
+static bool lanczos_bounds(const CgHistory &h, double *lo, double *hi) {
+  std::vector<double> d, e;
+  double alpha_prev = 0.0;
+  for (size_t j = 0; j < h.rho.size(); ++j) {
+    const double rho = h.rho[j], pv = h.pv[j];
+    if (!(rho > 0.0) || !(pv > 0.0) || !std::isfinite(rho) || !std::isfinite(pv)) break;
+    const double alpha = rho / pv;
+    const double beta = j > 0 ? rho / h.rho[j - 1] : 0.0;
+    if (j > 0) e.push_back(std::sqrt(beta) / alpha_prev);
+    d.push_back(1.0 / alpha + (j > 0 ? beta / alpha_prev : 0.0));
+    alpha_prev = alpha;
+  }
+  if (d.size() < 3) return false;
+  e.resize(d.size() - 1);
+  tridiag_extremes(d, e, lo, hi);
+  return *lo > 0.0 && *hi > *lo && std::isfinite(*hi);
+}
+static void mass_cheb_kernels(fdal_ctx *c, MassCheb &mc, CgWs &w, const DevCsr &M, const double *invdiag,
+                              const double *b, double *x) {
+  // iterate ping-pongs between w.x and w.v, d lives in w.p; the last step writes x
+  const int64_t n = w.n;
+  double *cur = w.x;
+  k_cheb_zero<<<grid_elems(c, std::max<int64_t>(n, 1)), kBlock, 0, c->stream>>>(n, b, invdiag, mc.coef[1], w.p,
+                                                                                 mc.its == 1 ? x : cur);
+  c->launches++;
+  for (int k = 1; k < mc.its; ++k) {
+    double *dst = k + 1 == mc.its ? x : (cur == w.x ? w.v : w.x);
+    EpiCheb<false> e{b, invdiag, cur, w.p, dst, mc.coef[2 * (size_t)k], mc.coef[2 * (size_t)k + 1], 0};
+    spmv(c, M, cur, e);
+    cur = dst;
+  }
+}
+// x = M^-1 b, Chebyshev mode 1.  The graph is pointer-bound, so the operands are staged through w.bin / w.z
+// (two m-vector copies) like the fixed-count PCG does.
+static void mass_cheb_solve1(fdal_ctx *c, MassCheb &mc, CgWs &w, const DevCsr &M, const double *invdiag,
+                             const double *b, double *x) {
+  if (graphs_enabled(c) && mc.graph_ok && !stream_is_capturing(c)) {
+    if (!mc.exec)
+      mc.graph_ok = capture_graph(c, [&]() { mass_cheb_kernels(c, mc, w, M, invdiag, w.bin, w.z); }, &mc.exec,
+                                  &mc.exec_nodes);
+    if (mc.exec) {
+      dcopy(c, w.n, b, w.bin);
+      if (cudaGraphLaunch(mc.exec, c->stream) != cudaSuccess && !c->fail) c->fail = FDAL_ERR_CUDA;
+      c->launches += mc.exec_nodes;
+      c->graph_launches++;
+      dcopy(c, w.n, w.z, x);
+      return;
+    }
+  }
+  mass_cheb_kernels(c, mc, w, M, invdiag, b, x);
+}
+// y = a * M^-repeat b (+ add), Chebyshev mode 2: one persistent kernel
+static void mass_cheb_solve2(fdal_ctx *c, MassCheb &mc, const DevCsr &M, const double *invdiag, int repeat, double a,
+                             const double *b, const double *add, double *y) {
+  cudaMemsetAsync(mc.bar, 0, sizeof(unsigned int), c->stream);  // arrivals only: the give-up flag bar[1] is sticky
+  k_mass_cheb_grid<<<mc.grid, kBlock, mc.smem, c->stream>>>(M.d, invdiag, mc.d_coef, mc.its, repeat, a, b, add, y,
+                                                            mc.xbuf, mc.bar, mc.rpc, mc.nnz_cap);
+  c->launches++;
+  launch_check(c);
+}
+// Decide whether (and how) the exact solve with M runs as a Chebyshev iteration: bounds from the
+// calibration CG, iteration count from the Chebyshev error bound, then a check of the true residual
+// on the calibration right-hand side (still in w.bin).  Anything unexpected keeps the Jacobi-PCG.
+static int mass_cheb_setup(fdal_ctx *c, MassCheb &mc, CgWs &w, const DevCsr &M, const double *invdiag,
+                           const CgHistory &h) {
+  const char *env = getenv("FDAL_MASS_CHEB");  // 0: Jacobi-PCG, 1: one kernel per iteration, 2 (default): persistent
+  const int want = env ? atoi(env) : 2;
+  mc.mode = 0;
+  if (want <= 0 || w.dist || w.n < 2 || M.use_bsr) return FDAL_OK;
+  double lo, hi;
+  if (!lanczos_bounds(h, &lo, &hi)) return FDAL_OK;
+  // Ritz values lie inside the spectrum: widen by 3 % on either side (costs ~2 iterations)
+  mc.lo = 0.97 * lo;
+  mc.hi = 1.03 * hi;
+  const double theta = 0.5 * (mc.hi + mc.lo), delta = 0.5 * (mc.hi - mc.lo), s1 = theta / delta;
+  const double sk = std::sqrt(mc.hi / mc.lo), q = (sk - 1.0) / (sk + 1.0);
+  const int cap = c->cfg.exact_mass_max_its > 0 ? c->cfg.exact_mass_max_its : 300;
+  int its = (int)std::ceil(std::log(2.0e16) / -std::log(q)) + 2;  // 2 q^k / (1 + q^2k) <= 1e-16
+  if (its > cap) return FDAL_OK;
+  its = std::max(its, 2);
+  mc.its = its;
+  mc.coef.assign(2 * (size_t)its, 0.0);
+  mc.coef[1] = 1.0 / theta;
+  double rho = 1.0 / s1;
+  for (int k = 1; k < its; ++k) {
+    const double rho1 = 1.0 / (2.0 * s1 - rho);
+    mc.coef[2 * (size_t)k] = rho1 * rho;
+    mc.coef[2 * (size_t)k + 1] = 2.0 * rho1 / delta;
+    rho = rho1;
+  }
+  int st;
+  int mode = 1;
+  if (want >= 2 && M.d.nnz < (1ll << 31)) {
+    // persistent kernel: at most one CTA per SM, >= 128 rows each (FDAL_MASS_CHEB_RPC: test knob, so that
+    // small problems exercise the grid barrier too); every CTA's slice must fit shared memory
+    const int n = (int)w.n;
+    const char *rpc_env = getenv("FDAL_MASS_CHEB_RPC");
+    const int min_rpc = rpc_env && atoi(rpc_env) > 0 ? atoi(rpc_env) : 128;
+    int grid = std::max(1, std::min(c->sms, (n + min_rpc - 1) / min_rpc));
+    const int rpc = (n + grid - 1) / grid;
+    grid = (n + rpc - 1) / rpc;
+    std::vector<int> hrp((size_t)n + 1);
+    CU(cudaMemcpyAsync(hrp.data(), M.rp, ((size_t)n + 1) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    int nnz_cap = 0;
+    for (int j = 0; j < grid; ++j)
+      nnz_cap = std::max(nnz_cap, hrp[(size_t)std::min(n, (j + 1) * rpc)] - hrp[(size_t)std::min(n, j * rpc)]);
+    nnz_cap = (nnz_cap + 1) & ~1;
+    const size_t smem = (size_t)rpc * 4 * sizeof(double) + (size_t)nnz_cap * (sizeof(double) + sizeof(int)) +
+                        ((size_t)rpc + 2) * sizeof(int);
+    int dev = 0, max_optin = 0;
+    CU(cudaGetDevice(&dev));
+    CU(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    if (smem <= (size_t)max_optin) {
+      // the opt-in maximum, not `smem`: M and Mp may both use the kernel with different slice sizes
+      CU(cudaFuncSetAttribute(k_mass_cheb_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+      int per_sm = 0;
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mass_cheb_grid, kBlock, smem));
+      if (per_sm >= 1) {  // co-residency of the whole grid: the barrier's precondition
+        mc.grid = grid;
+        mc.rpc = rpc;
+        mc.nnz_cap = nnz_cap;
+        mc.smem = smem;
+        if ((st = dvec(c, &mc.d_coef, 2 * (int64_t)its))) return st;
+        if ((st = dvec(c, &mc.xbuf, 2 * (int64_t)n))) return st;
+        if ((st = dmalloc(c, &mc.bar, 2))) return st;
+        CU(cudaMemsetAsync(mc.bar, 0, 2 * sizeof(unsigned int), c->stream));
+        CU(cudaMemcpyAsync(mc.d_coef, mc.coef.data(), mc.coef.size() * sizeof(double), cudaMemcpyHostToDevice,
+                           c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        mode = 2;
+      }
+    }
+  }
+  // verification on the calibration right-hand side
+  mc.mode = mode;
+  if (mode == 2)
+    mass_cheb_solve2(c, mc, M, invdiag, 1, 1.0, w.bin, nullptr, w.z);
+  else
+    mass_cheb_kernels(c, mc, w, M, invdiag, w.bin, w.z);
+  spmv(c, M, w.z, EpiResid{w.r, w.bin});
+  dot(c, w.n, w.r, w.r, w.scal + S_RR, false);
+  dot(c, w.n, w.bin, w.bin, w.scal + S_RHO, false);
+  double sc[4];
+  if ((st = read_scalars(c, w.scal, 4, sc))) return st;
+  mc.verified_resid = std::sqrt(std::fabs(sc[S_RR]) / std::max(sc[S_RHO], 1e-300));
+  if (mode == 2) {
+    unsigned int gave_up = 0;
+    CU(cudaMemcpy(&gave_up, mc.bar + 1, sizeof(gave_up), cudaMemcpyDeviceToHost));
+    if (gave_up) mc.verified_resid = std::numeric_limits<double>::infinity();
+  }
+  if (!(mc.verified_resid <= 2e-14)) {
+    set_err(c, "warning: the Chebyshev mass solve (%d iterations on [%.4g, %.4g]) left a relative residual of %.2e: "
+               "keeping the Jacobi-PCG", its, mc.lo, mc.hi, mc.verified_resid);
+    mc.mode = 0;
+  }
+  return FDAL_OK;
+}
+// x = M^-1 b through whichever form was selected at fdal_finalize
+static void mass_solve(fdal_ctx *c, MassCheb &mc, CgWs &w, const DevCsr &M, const double *invdiag, int pcg_its,
+                       const double *b, double *x) {
+  if (mc.mode == 2)
+    mass_cheb_solve2(c, mc, M, invdiag, 1, 1.0, b, nullptr, x);
+  else if (mc.mode == 1)
+    mass_cheb_solve1(c, mc, w, M, invdiag, b, x);
+  else
+    mass_solve_fixed(c, w, M, invdiag, pcg_its, b, x);
 }
 
 // ------------------------------------------------------------------ operators of the path
@@ -1101,11 +1340,15 @@ static void apply_winv_scaled(fdal_ctx *c, double a, const double *x, double *y,
     c->launches++;
     return;
   }
+  if (c->mcheb_m.mode == 2) {  // whole solve(s), scaling and the add in one persistent kernel
+    mass_cheb_solve2(c, c->mcheb_m, c->dmat[FDAL_MAT_M], c->d_m_invdiag, repeat, a, x, add, y);
+    return;
+  }
   if (repeat == 1) {
-    mass_solve_fixed(c, c->cgmass_m, c->dmat[FDAL_MAT_M], c->d_m_invdiag, c->mass_its_m, x, y);
+    mass_solve(c, c->mcheb_m, c->cgmass_m, c->dmat[FDAL_MAT_M], c->d_m_invdiag, c->mass_its_m, x, y);
   } else {
-    mass_solve_fixed(c, c->cgmass_m, c->dmat[FDAL_MAT_M], c->d_m_invdiag, c->mass_its_m, x, c->t_mw);
-    mass_solve_fixed(c, c->cgmass_m, c->dmat[FDAL_MAT_M], c->d_m_invdiag, c->mass_its_m, c->t_mw, y);
+    mass_solve(c, c->mcheb_m, c->cgmass_m, c->dmat[FDAL_MAT_M], c->d_m_invdiag, c->mass_its_m, x, c->t_mw);
+    mass_solve(c, c->mcheb_m, c->cgmass_m, c->dmat[FDAL_MAT_M], c->d_m_invdiag, c->mass_its_m, c->t_mw, y);
   }
   dscale(c, m, a, y);
   if (add) axpby(c, m, 1.0, add, 1.0, y);
@@ -1113,7 +1356,7 @@ static void apply_winv_scaled(fdal_ctx *c, double a, const double *x, double *y,
 // Mp_inv (stokes_immersed_boundary.cc:931-963)
 static int apply_mp_inv(fdal_ctx *c, const double *x, double *y) {
   if (c->cfg.mp_inv_mode == FDAL_MPINV_EXACT) {
-    mass_solve_fixed(c, c->cgmass_p, c->dmat[FDAL_MAT_MP], c->d_mp_invdiag, c->mass_its_p, x, y);
+    mass_solve(c, c->mcheb_p, c->cgmass_p, c->dmat[FDAL_MAT_MP], c->d_mp_invdiag, c->mass_its_p, x, y);
     return FDAL_OK;
   }
   OpFn op = [&](const double *in, double *out, double *d) { spmv(c, c->dmat[FDAL_MAT_MP], in, EpiDotX{out, in}, d); };
@@ -2037,6 +2280,8 @@ void fdal_destroy(fdal_ctx *c) {
     if (w->body_exec) cudaGraphExecDestroy(w->body_exec);
     if (w->fixed_exec) cudaGraphExecDestroy(w->fixed_exec);
   }
+  for (MassCheb *mc : {&c->mcheb_m, &c->mcheb_p})
+    if (mc->exec) cudaGraphExecDestroy(mc->exec);
   for (void *p : c->allocs) cudaFree(p);
   for (int q = 0; q < (int)c->peer_arena.size(); ++q)
     if (q != c->rank && c->peer_arena[(size_t)q]) cudaIpcCloseMemHandle(c->peer_arena[(size_t)q]);
@@ -2346,16 +2591,25 @@ int fdal_finalize(fdal_ctx *c) {
   if (c->cfg.winv_mode != FDAL_WINV_DIAG) {
     if ((st = alloc_cg(c, c->cgmass_m, c->m))) return st;
     if ((st = invdiag_of(c, c->dmat[FDAL_MAT_M], &c->d_m_invdiag))) return st;
-    if ((st = mass_calibrate(c, c->cgmass_m, c->dmat[FDAL_MAT_M], c->d_m_invdiag, &c->mass_its_m))) return st;
+    CgHistory hist_m;
+    if ((st = mass_calibrate(c, c->cgmass_m, c->dmat[FDAL_MAT_M], c->d_m_invdiag, &c->mass_its_m, &hist_m))) return st;
+    // multiplier spaces too large for one CTA / a dense inverse: Chebyshev form (elliptic_interface, co-dimension 0)
+    // (FDAL_MASS_CHEB_MIN_ROWS: test knob, lets small problems take this path)
+    const char *cmin = getenv("FDAL_MASS_CHEB_MIN_ROWS");
+    if (c->m > (cmin ? atoll(cmin) : (long long)kMassCtaMaxRows) &&
+        (st = mass_cheb_setup(c, c->mcheb_m, c->cgmass_m, c->dmat[FDAL_MAT_M], c->d_m_invdiag, hist_m)))
+      return st;
     static const bool no_cta = getenv("FDAL_NO_MASS_CTA") != nullptr;
-    if (c->m <= kMassCtaMaxRows && !no_cta) {
+    if (c->m <= kMassCtaMaxRows && !no_cta && c->mcheb_m.mode == 0) {
       if ((st = dvec(c, &c->mass_cta_ws, 5 * c->m))) return st;
       CU(cudaFuncSetAttribute(k_mass_pcg_cta<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)(4 * kMassCtaSmemRows * sizeof(double))));
     }
     // small multiplier spaces: the exact W^-1 as ONE L2-resident dense GEMV (FDAL_DENSE_WINV=0: keep the PCG)
     const char *dw = getenv("FDAL_DENSE_WINV");
-    if ((!dw || atoi(dw) > 0) && c->m > 0 && c->m <= kDenseWinvMaxRows && (st = build_dense_winv(c))) return st;
+    if ((!dw || atoi(dw) > 0) && c->m > 0 && c->m <= kDenseWinvMaxRows && c->mcheb_m.mode == 0 &&
+        (st = build_dense_winv(c)))
+      return st;
   }
   if (is_stokes(c)) {
     if ((st = alloc_cg(c, c->cgmass_p, c->n1))) return st;
@@ -2363,7 +2617,10 @@ int fdal_finalize(fdal_ctx *c) {
     c->cgmass_p.n_dot = c->n1;
     if (c->cfg.mp_inv_mode == FDAL_MPINV_EXACT) {
       if ((st = invdiag_of(c, c->dmat[FDAL_MAT_MP], &c->d_mp_invdiag))) return st;
-      if ((st = mass_calibrate(c, c->cgmass_p, c->dmat[FDAL_MAT_MP], c->d_mp_invdiag, &c->mass_its_p))) return st;
+      CgHistory hist_p;
+      if ((st = mass_calibrate(c, c->cgmass_p, c->dmat[FDAL_MAT_MP], c->d_mp_invdiag, &c->mass_its_p, &hist_p)))
+        return st;
+      if ((st = mass_cheb_setup(c, c->mcheb_p, c->cgmass_p, c->dmat[FDAL_MAT_MP], c->d_mp_invdiag, hist_p))) return st;
     } else {
       if ((st = dvec(c, &c->d_mp_lumped, c->n1))) return st;
       if ((int64_t)c->h_mp_lumped.size() == c->n1) {
@@ -2748,6 +3005,32 @@ int fdal_comm_init(fdal_ctx *c, const char id[128], int rank, int n_ranks) {
   return FDAL_OK;
 }
 int fdal_comm_mode(const fdal_ctx *c) { return c ? (c->nranks <= 1 ? 0 : (c->p2p ? 2 : 1)) : -1; }
+int fdal_mass_solver_info(const fdal_ctx *c, int which, int32_t *form, int32_t *iterations, double *interval_lo,
+                          double *interval_hi, double *verified_residual) {
+  if (!c || !c->finalized || which < 0 || which > 1) return FDAL_ERR_STATE;
+  const MassCheb &mc = which == 0 ? c->mcheb_m : c->mcheb_p;
+  const bool exact = which == 0 ? c->cfg.winv_mode != FDAL_WINV_DIAG
+                                : (is_stokes(c) && c->cfg.mp_inv_mode == FDAL_MPINV_EXACT);
+  int f = FDAL_MASS_NONE, its = 0;
+  if (exact) {
+    if (mc.mode == 2)
+      f = FDAL_MASS_CHEB_PERSISTENT, its = mc.its;
+    else if (mc.mode == 1)
+      f = FDAL_MASS_CHEB_KERNELS, its = mc.its;
+    else if (which == 0 && c->d_winv_dense)
+      f = FDAL_MASS_DENSE;
+    else if (which == 0 && c->mass_cta_ws)
+      f = FDAL_MASS_PCG_ONE_CTA, its = c->mass_its_m;
+    else
+      f = FDAL_MASS_PCG_KERNELS, its = which == 0 ? c->mass_its_m : c->mass_its_p;
+  }
+  if (form) *form = f;
+  if (iterations) *iterations = its;
+  if (interval_lo) *interval_lo = mc.mode ? mc.lo : 0.0;
+  if (interval_hi) *interval_hi = mc.mode ? mc.hi : 0.0;
+  if (verified_residual) *verified_residual = mc.mode ? mc.verified_resid : 0.0;
+  return FDAL_OK;
+}
 int fdal_set_halo(fdal_ctx *c, int matrix_id, int level, int which, int64_t n_owned_cols, int64_t n_halo,
                   const int32_t *send_counts, const int32_t *send_idx, const int32_t *recv_counts) {
   CHECK_CTX(c);

@@ -558,8 +558,11 @@ struct BsrDev {
   int aos = 0;
 };
 
+// 3x3 blocks, one block per lane in flight: 8 CTAs/SM (32 registers) for every epilogue.  Without the bound the
+// epilogue with the fused reduction (EpiCheb<true>) took 40 registers -> 6 CTAs/SM -> 565 us against 505 us for
+// the same step without the reduction (profiles/r2_ncu_full_k_bsr_spmv_stokes3d_nel40.md); no variant spills.
 template <int B, int TPR, class Epi, bool TWO, int U = 1, bool DIST = false>
-__global__ void __launch_bounds__(kBlock) k_bsr_spmv(BsrDev A, XVec X, CsrDev C2, const double *__restrict__ t2, Epi epi,
+__global__ void __launch_bounds__(kBlock, (B == 3 && U == 1) ? 8 : 1) k_bsr_spmv(BsrDev A, XVec X, CsrDev C2, const double *__restrict__ t2, Epi epi,
                                                       Reducer R) {
   __shared__ double smem[32];
   constexpr int rows_per_block = kBlock / TPR;
@@ -918,6 +921,108 @@ __global__ void __launch_bounds__(kMassCtaThreads) k_mass_pcg_cta(CsrDev M, cons
     }
   }
   for (int i = tid; i < n; i += nt) y[i] = a * x[i] + (add ? add[i] : 0.0);
+}
+
+// ---- whole fixed-count Chebyshev mass solve in ONE persistent multi-CTA kernel (K5 for mass matrices
+// too large for one CTA: the co-dimension-0 multiplier space of elliptic_interface, m = 2e4..1e5; the
+// 2-D pressure space of stokes_immersed_boundary) --------------------------------------------------
+// As separate kernels a Jacobi-PCG mass solve is 4 launches per iteration of ~1 us of work each
+// (configs[2]: 244 launches = 0.93 ms per augmented apply, 2.7 % of the HBM roofline).  Chebyshev needs
+// no inner products: with the spectral interval of D^-1 M known (Lanczos bounds from the calibration run
+// at fdal_finalize) iteration k is  r = b - M x ; d = c1_k d + c2_k D^-1 r ; x += d,  and the only
+// coupling between rows is the gather of x.  So: CTA j owns rows [j*rpc, (j+1)*rpc); its slice of M
+// (row pointers, columns, values) is staged ONCE into shared memory (the host only picks this kernel
+// when every slice fits; larger matrices are bandwidth-bound and take one fused SpMV kernel per
+// iteration), d, b, D^-1 and the own part of x stay in shared memory for the whole solve, the iterate is
+// double-buffered in global memory (L2-resident), and the CTAs meet at one grid barrier per iteration.
+// The grid is at most one CTA per SM, so all CTAs are co-resident and the barrier cannot deadlock
+// (`bar` is zeroed by a memset node in front of the launch).  coef[2k], coef[2k+1] = c1_k, c2_k.
+__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int *p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// bar[0]: arrivals (monotonic over the launch), bar[1]: set when a CTA gave up waiting.  The wait is bounded
+// (~2 s of SM clocks): should the co-residency assumption ever be violated the kernel ends with a wrong
+// result and the flag raised — the host checks it when it verifies the solve at fdal_finalize — instead of
+// hanging the device.
+__device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();  // cumulative: the block's stores (ordered by the barrier above) before the arrival
+    atomicAdd(bar, 1u);
+    const long long t0 = clock64();
+    while (ld_acquire_gpu_u32(bar) < target) {
+      if (clock64() - t0 > 4000000000ll) {
+        atomicExch(bar + 1, 1u);
+        break;
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+__global__ void __launch_bounds__(kBlock) k_mass_cheb_grid(CsrDev M, const double *__restrict__ invd,
+                                                            const double *__restrict__ coef, int its, int repeat,
+                                                            double a, const double *__restrict__ b,
+                                                            const double *__restrict__ add, double *__restrict__ y,
+                                                            double *xbuf /* [2][n] */, unsigned int *bar,
+                                                            int rpc, int nnz_cap) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n = M.nrows;
+  const int r0 = min(n, (int)blockIdx.x * rpc), r1 = min(n, r0 + rpc);
+  const int nr = r1 - r0;
+  double *sd = reinterpret_cast<double *>(smem_raw);
+  double *sb = sd + rpc, *sinv = sb + rpc, *sx = sinv + rpc;
+  double *sv = sx + rpc;                                  // [nnz_cap]
+  int *sci = reinterpret_cast<int *>(sv + nnz_cap);       // [nnz_cap]
+  int *srp = sci + nnz_cap;                               // [rpc + 1]
+  const int tid = threadIdx.x;
+  {
+    const int kbase = __ldg(M.rp + r0), kend = __ldg(M.rp + r1);
+    for (int k = kbase + tid; k < kend; k += kBlock) {
+      sv[k - kbase] = __ldg(M.v + k);
+      sci[k - kbase] = __ldg(M.ci + k);
+    }
+    for (int i = tid; i <= nr; i += kBlock) srp[i] = __ldg(M.rp + r0 + i) - kbase;
+  }
+  for (int i = tid; i < nr; i += kBlock) sinv[i] = __ldg(invd + r0 + i);
+  __syncthreads();
+  unsigned int gen = 0;
+  for (int rep = 0; rep < repeat; ++rep) {
+    int p = 0;
+    {  // step 0 from the zero guess: d = c2_0 D^-1 b ; x = d
+      const double c2 = __ldg(coef + 1);
+      for (int i = tid; i < nr; i += kBlock) {
+        const double bi = rep == 0 ? b[r0 + i] : sx[i];  // W = M^2: the second solve's right-hand side is x
+        const double dv = c2 * sinv[i] * bi;
+        sb[i] = bi;
+        sd[i] = dv;
+        sx[i] = dv;
+        xbuf[r0 + i] = dv;
+      }
+    }
+    for (int k = 1; k < its; ++k) {
+      grid_barrier(bar, ++gen * gridDim.x);
+      const double c1 = __ldg(coef + 2 * k), c2 = __ldg(coef + 2 * k + 1);
+      const double *xin = xbuf + (size_t)p * n;
+      double *xout = xbuf + (size_t)(p ^ 1) * n;
+      for (int i = tid; i < nr; i += kBlock) {
+        double s = 0.0;
+        const int k1 = srp[i + 1];
+        for (int kk = srp[i]; kk < k1; ++kk) s += sv[kk] * __ldcg(xin + sci[kk]);  // L2: written by other CTAs
+        const double dv = c1 * sd[i] + c2 * sinv[i] * (sb[i] - s);
+        const double xo = sx[i] + dv;
+        sd[i] = dv;
+        sx[i] = xo;
+        xout[r0 + i] = xo;
+      }
+      p ^= 1;
+    }
+    // the next repeat overwrites buffer 0 while slower CTAs may still gather from it
+    if (rep + 1 < repeat) grid_barrier(bar, ++gen * gridDim.x);
+  }
+  for (int i = tid; i < nr; i += kBlock) y[r0 + i] = a * sx[i] + (add ? add[r0 + i] : 0.0);
 }
 
 // y = a x + b y   (a, b host scalars; x may alias y only if a-term unused)

@@ -306,6 +306,24 @@ int fdal_amg_set_coarse_range(fdal_ctx *ctx, int which, int64_t lo, int64_t hi);
  * library's own kernels (fused into the reductions' last block / the SpMV's boundary chunks) */
 int fdal_comm_mode(const fdal_ctx *ctx);
 
+/* How the exact mass inverses (the device replacement of SparseDirectUMFPACK::vmult: immersed_laplace.cc:864,
+ * 875-876; stokes_immersed_boundary.cc:960-962, 981-985; elliptic_interface.cc:719-720, 736-737) are applied,
+ * decided at fdal_finalize.  which = 0: the multiplier mass matrix M (W^-1 = M^-1 or M^-2), 1: the pressure
+ * mass matrix Mp.  *iterations: the fixed iteration count of one solve (0 for the dense form);
+ * [*interval_lo, *interval_hi]: the spectral interval of D^-1 M the Chebyshev coefficients were built on;
+ * *verified_residual: |b - M x| / |b| of the Chebyshev solve on the calibration right-hand side (it must be
+ * <= 2e-14 for the Chebyshev form to be selected).  Any out pointer may be NULL. */
+enum {
+  FDAL_MASS_NONE = 0,            /* no exact mass solve in this configuration */
+  FDAL_MASS_PCG_KERNELS = 1,     /* fixed-count Jacobi-PCG, four kernels per iteration, one CUDA graph */
+  FDAL_MASS_PCG_ONE_CTA = 2,     /* the same iteration inside one CTA (m <= 16384) */
+  FDAL_MASS_DENSE = 3,           /* dense W^-1 GEMV (m <= 4096) */
+  FDAL_MASS_CHEB_KERNELS = 4,    /* fixed-count Chebyshev, one fused SpMV kernel per iteration */
+  FDAL_MASS_CHEB_PERSISTENT = 5  /* fixed-count Chebyshev in one persistent kernel, matrix staged in shared memory */
+};
+int fdal_mass_solver_info(const fdal_ctx *ctx, int which, int32_t *form, int32_t *iterations, double *interval_lo,
+                          double *interval_hi, double *verified_residual);
+
 /* ---- setup phase on the device -----------------------------------
  * Operator-form AL term (immersed_laplace.cc:659-702 with the particles of utilities.h:755-837;
  * nitsche_bcs.cc:517-572):  A += sum_q weight[q] * phi_q phi_q^T  scattered into the CSR values of the
