@@ -30,10 +30,16 @@ _lib = None
 
 
 def build_host_lib(force=False):
-    src = os.path.join(_HERE, "csrc", "host_setup.c")
-    if force or not os.path.exists(_HOST_LIB) or os.path.getmtime(_HOST_LIB) < os.path.getmtime(src):
+    csrc = os.path.join(_HERE, "csrc")
+    src = os.path.join(csrc, "host_setup.c")
+    # the host half of fdal_finalize (csrc/host_finalize.h) rides along so the CPU tests can call it
+    hooks = os.path.join(csrc, "host_finalize_hooks.cpp")
+    deps = [src, hooks, os.path.join(csrc, "host_finalize.h")]
+    if force or not os.path.exists(_HOST_LIB) or any(os.path.getmtime(_HOST_LIB) < os.path.getmtime(d) for d in deps):
+        obj = os.path.join(csrc, "host_setup.o")
+        subprocess.run(["/usr/bin/gcc", "-O3", "-fopenmp", "-fPIC", "-c", "-o", obj, src], check=True, capture_output=True)
         subprocess.run(
-            ["/usr/bin/gcc", "-O3", "-fopenmp", "-fPIC", "-shared", "-o", _HOST_LIB, src], check=True,
+            ["/usr/bin/g++", "-O3", "-std=c++17", "-fopenmp", "-fPIC", "-shared", "-o", _HOST_LIB, hooks, obj], check=True,
             capture_output=True
         )
     return _HOST_LIB

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB = os.path.join(CSRC, "libfdal.so")
 SOURCES = ["fdal.cu", "setup.cu"]
-HEADERS = ["kernels.cuh", os.path.join("..", "..", "include", "fdal.h")]
+HEADERS = ["kernels.cuh", "host_finalize.h", os.path.join("..", "..", "include", "fdal.h")]
 
 
 def nvcc_path():

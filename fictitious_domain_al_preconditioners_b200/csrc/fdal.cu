@@ -19,10 +19,14 @@
 #include <cstring>
 #include <functional>
 #include <limits>
+#include <memory>
+#include <omp.h>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/fdal.h"
+#include "host_finalize.h"
 #include "kernels.cuh"
 
 namespace fdal {
@@ -67,39 +71,6 @@ static NcclApi *nccl_api() {
   api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.AllGather && api.Send && api.Recv &&
            api.GroupStart && api.GroupEnd;
   return &api;
-}
-
-// ------------------------------------------------------------------ host CSR
-struct HostCsr {
-  int64_t nr = 0, nc = 0, nnz = 0;
-  std::vector<int> rp, ci;
-  std::vector<double> v;
-  bool set = false;
-  // halo plan (multi-GPU): columns [0, n_owned) are owned, [n_owned, n_owned + n_halo) halo
-  bool has_plan = false;
-  int64_t n_owned = 0, n_halo = 0;
-  std::vector<int> send_counts, recv_counts, send_idx;
-  int64_t owned_cols() const { return has_plan ? n_owned : nc; }
-};
-static void host_transpose(const HostCsr &A, HostCsr &T) {
-  // stable counting sort: within a row of T columns ascend, i.e. the same
-  // accumulation order as SparseMatrix::Tvmult's row scatter
-  T.nr = A.nc;
-  T.nc = A.nr;
-  T.nnz = A.nnz;
-  T.rp.assign(T.nr + 1, 0);
-  T.ci.resize(A.nnz);
-  T.v.resize(A.nnz);
-  for (int64_t k = 0; k < A.nnz; ++k) T.rp[A.ci[k] + 1]++;
-  for (int64_t i = 0; i < T.nr; ++i) T.rp[i + 1] += T.rp[i];
-  std::vector<int> pos(T.rp.begin(), T.rp.end() - 1);
-  for (int64_t i = 0; i < A.nr; ++i)
-    for (int k = A.rp[i]; k < A.rp[i + 1]; ++k) {
-      const int q = pos[A.ci[k]]++;
-      T.ci[q] = (int)i;
-      T.v[q] = A.v[k];
-    }
-  T.set = true;
 }
 
 // one exchange channel (kernels.cuh: ChanDev) as the host sees it
@@ -343,53 +314,11 @@ static int choose_tpr(double avg) {
 // (and leaves d untouched) when blocking would store too many explicit zeros.
 static int build_bsr(fdal_ctx *c, const HostCsr &h, int b, DevCsr &d, bool *done) {
   *done = false;
-  if (b < 2 || b > 3 || h.nr % b || h.nc % b || h.owned_cols() % b || h.nr == 0) return FDAL_OK;
+  IntBuf brp, bcj;
+  DblBuf bv;
+  if (!host_bsr_convert(h, b, 1.35, brp, bcj, bv)) return FDAL_OK;
   const int64_t nbr = h.nr / b;
-  std::vector<int> brp((size_t)nbr + 1, 0);
-#pragma omp parallel
-  {
-    std::vector<int> tmp;
-#pragma omp for schedule(dynamic, 2048)
-    for (int64_t I = 0; I < nbr; ++I) {
-      tmp.clear();
-      for (int r = 0; r < b; ++r)
-        for (int k = h.rp[I * b + r]; k < h.rp[I * b + r + 1]; ++k) tmp.push_back(h.ci[k] / b);
-      std::sort(tmp.begin(), tmp.end());
-      brp[(size_t)I + 1] = (int)(std::unique(tmp.begin(), tmp.end()) - tmp.begin());
-    }
-  }
-  int64_t nblk = 0;
-  for (int64_t I = 0; I < nbr; ++I) {
-    nblk += brp[(size_t)I + 1];
-    if (nblk >= (int64_t)std::numeric_limits<int>::max() / (b * b)) return FDAL_OK;
-    brp[(size_t)I + 1] = (int)nblk;
-  }
-  if ((double)nblk * b * b > 1.35 * (double)h.nnz) return FDAL_OK;  // too much zero fill: stay scalar
-  std::vector<int> bcj((size_t)nblk);
-  std::vector<double> bv((size_t)nblk * b * b, 0.0);
-  // blocks stored contiguously (AoS): measured 25-40 % faster on B200 than per-row planes (profiles/)
-#pragma omp parallel
-  {
-    std::vector<int> tmp;
-#pragma omp for schedule(dynamic, 2048)
-    for (int64_t I = 0; I < nbr; ++I) {
-      tmp.clear();
-      for (int r = 0; r < b; ++r)
-        for (int k = h.rp[I * b + r]; k < h.rp[I * b + r + 1]; ++k) tmp.push_back(h.ci[k] / b);
-      std::sort(tmp.begin(), tmp.end());
-      tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
-      const int k0 = brp[(size_t)I];
-      const int nb = (int)tmp.size();
-      for (int k = 0; k < nb; ++k) bcj[(size_t)k0 + k] = tmp[k];
-      double *vb = bv.data() + (size_t)k0 * b * b;
-      for (int r = 0; r < b; ++r)
-        for (int k = h.rp[I * b + r]; k < h.rp[I * b + r + 1]; ++k) {
-          const int J = h.ci[k] / b, q = h.ci[k] % b;
-          const int pos = (int)(std::lower_bound(tmp.begin(), tmp.end(), J) - tmp.begin());
-          vb[(size_t)pos * b * b + (r * b + q)] += h.v[k];
-        }
-    }
-  }
+  const int64_t nblk = brp[(size_t)nbr];
   int *drp = nullptr, *dcj = nullptr;
   double *dv = nullptr;
   int st;
@@ -1200,8 +1129,13 @@ static void mass_cheb_solve2(fdal_ctx *c, MassCheb &mc, const DevCsr &M, const d
 // on the calibration right-hand side (still in w.bin).  Anything unexpected keeps the Jacobi-PCG.
 static int mass_cheb_setup(fdal_ctx *c, MassCheb &mc, CgWs &w, const DevCsr &M, const double *invdiag,
                            const CgHistory &h) {
-  const char *env = getenv("FDAL_MASS_CHEB");  // 0: Jacobi-PCG, 1: one kernel per iteration, 2 (default): persistent
-  const int want = env ? atoi(env) : 2;
+  // FDAL_MASS_CHEB = 0: Jacobi-PCG, 1 (default): one fused kernel per iteration, 2: the persistent kernel.
+  // Measured on B200 (profiles/r2_mass_chebyshev.md, elliptic_interface cycle 6, m = 20 609, 58 iterations): one
+  // augmented apply 928 us with the Jacobi-PCG (244 launches), 220 us with one kernel per iteration, 267 us with the
+  // persistent kernel — a grid barrier through L2 (store, fence, arrive, poll, gather: four dependent L2 round
+  // trips, ~4 us) costs more than a CUDA-graph kernel node (~2.9 us), so the graph is the default.
+  const char *env = getenv("FDAL_MASS_CHEB");
+  const int want = env ? atoi(env) : 1;
   mc.mode = 0;
   if (want <= 0 || w.dist || w.n < 2 || M.use_bsr) return FDAL_OK;
   double lo, hi;
@@ -2341,25 +2275,6 @@ static int check_csr(fdal_ctx *c, const char *what, int64_t nr, int64_t nc, int6
   }
   return FDAL_OK;
 }
-static void fill_host_csr(HostCsr &h, int64_t nr, int64_t nc, int64_t nnz, const int64_t *rp, const int32_t *ci,
-                          const double *v) {
-  h = HostCsr();
-  h.nr = nr;
-  h.nc = nc;
-  h.nnz = nnz;
-  h.rp.resize((size_t)nr + 1);
-  h.ci.resize((size_t)nnz);
-  h.v.resize((size_t)nnz);
-#pragma omp parallel for schedule(static)
-  for (int64_t i = 0; i <= nr; ++i) h.rp[(size_t)i] = (int)rp[i];
-#pragma omp parallel for schedule(static)
-  for (int64_t k = 0; k < nnz; ++k) {
-    h.ci[(size_t)k] = ci[k];
-    h.v[(size_t)k] = v[k];
-  }
-  h.set = true;
-}
-
 int fdal_set_csr(fdal_ctx *c, int id, int64_t nr, int64_t nc, int64_t nnz, const int64_t *rp, const int32_t *ci,
                  const double *v) {
   CHECK_CTX(c);
@@ -2533,9 +2448,9 @@ int fdal_finalize(fdal_ctx *c) {
   }
   for (int id = 0; id < FDAL_MAT_COUNT; ++id) {  // host copies no longer needed
     HostCsr &h = c->hmat[id];
-    std::vector<int>().swap(h.ci);
-    std::vector<double>().swap(h.v);
-    std::vector<int>().swap(h.rp);
+    IntBuf().swap(h.ci);
+    DblBuf().swap(h.v);
+    IntBuf().swap(h.rp);
   }
   for (int id : {FDAL_MAT_A, FDAL_MAT_BT, FDAL_MAT_B, FDAL_MAT_MP}) c->dmat[id].dist_rows = D;
   // AMG
@@ -2593,10 +2508,12 @@ int fdal_finalize(fdal_ctx *c) {
     if ((st = invdiag_of(c, c->dmat[FDAL_MAT_M], &c->d_m_invdiag))) return st;
     CgHistory hist_m;
     if ((st = mass_calibrate(c, c->cgmass_m, c->dmat[FDAL_MAT_M], c->d_m_invdiag, &c->mass_its_m, &hist_m))) return st;
-    // multiplier spaces too large for one CTA / a dense inverse: Chebyshev form (elliptic_interface, co-dimension 0)
+    // multiplier spaces too large for a dense inverse: Chebyshev form (elliptic_interface, co-dimension 0).  The
+    // single-CTA Jacobi-PCG that used to cover 4096 < m <= 16384 is 3x slower (cycle 5, m = 5 249: 2994 -> 954 ms
+    // per solve) and stays only as the FDAL_MASS_CHEB=0 fallback
     // (FDAL_MASS_CHEB_MIN_ROWS: test knob, lets small problems take this path)
     const char *cmin = getenv("FDAL_MASS_CHEB_MIN_ROWS");
-    if (c->m > (cmin ? atoll(cmin) : (long long)kMassCtaMaxRows) &&
+    if (c->m > (cmin ? atoll(cmin) : (long long)kDenseWinvMaxRows) &&
         (st = mass_cheb_setup(c, c->mcheb_m, c->cgmass_m, c->dmat[FDAL_MAT_M], c->d_m_invdiag, hist_m)))
       return st;
     static const bool no_cta = getenv("FDAL_NO_MASS_CTA") != nullptr;

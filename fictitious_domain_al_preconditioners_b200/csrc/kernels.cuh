@@ -562,7 +562,7 @@ struct BsrDev {
 // epilogue with the fused reduction (EpiCheb<true>) took 40 registers -> 6 CTAs/SM -> 565 us against 505 us for
 // the same step without the reduction (profiles/r2_ncu_full_k_bsr_spmv_stokes3d_nel40.md); no variant spills.
 template <int B, int TPR, class Epi, bool TWO, int U = 1, bool DIST = false>
-__global__ void __launch_bounds__(kBlock, (B == 3 && U == 1) ? 8 : 1) k_bsr_spmv(BsrDev A, XVec X, CsrDev C2, const double *__restrict__ t2, Epi epi,
+__global__ void __launch_bounds__(kBlock, (B == 3 && U == 1) ? 8 : 0) k_bsr_spmv(BsrDev A, XVec X, CsrDev C2, const double *__restrict__ t2, Epi epi,
                                                       Reducer R) {
   __shared__ double smem[32];
   constexpr int rows_per_block = kBlock / TPR;

@@ -4,6 +4,8 @@ stokes_immersed_boundary.cc:960-962 for the pressure mass matrix).  Both forms â
 iteration, and the persistent kernel with the matrix staged in shared memory and one grid barrier per
 iteration â€” against the oracle's sparse direct solves, on the small seeded cases (test knobs push them onto
 this path and split them over many CTAs) and at the size of the benched elliptic problem (default selection)."""
+import functools
+
 import numpy as np
 import pytest
 
@@ -13,6 +15,7 @@ from fictitious_domain_al_preconditioners_b200 import synthetic as syn
 
 from . import parity_log as PL
 from . import problems as P
+from .test_gpu_parity import TOL_SOLUTION, _self_sensitivity
 
 pytestmark = pytest.mark.gpu
 
@@ -46,16 +49,22 @@ def test_chebyshev_mass_solves_match_the_direct_solves(name, form, oracle_mod, m
     xg, ig = gpu.solve(rhs)
     xo, io = ora.solve(rhs)
     assert abs(ig.outer_iterations - io.outer_iterations) <= 1
-    PL.check("solution", P.relerr(xg, xo), 1e-8, outer=(ig.outer_iterations, io.outer_iterations))
+    if ig.outer_iterations == io.outer_iterations:
+        # the bar of test_gpu_parity.test_full_solve: 1e-10 unless the oracle's own solution moves more than that
+        # under a one-ulp perturbation of the right-hand side (unstable inner CG trajectories: the elliptic cases)
+        tol = max(TOL_SOLUTION, 50 * _self_sensitivity(lambda v: ora.solve(v)[0], rhs, 4))
+        PL.check("solution", P.relerr(xg, xo), tol, outer=(ig.outer_iterations, io.outer_iterations))
+    res = np.linalg.norm(ora.apply_system(xg) - rhs)
+    assert res <= 10 * max(prob.config.outer.tol, prob.config.outer.reduce * ig.initial_residual)
 
 
 def test_default_selection_and_off_switch(monkeypatch):
-    """Defaults: the small seeded cases keep the dense / single-CTA forms; FDAL_MASS_CHEB=0 keeps the Jacobi-PCG
-    for the pressure mass matrix."""
+    """Defaults: a small multiplier space keeps the dense form, the pressure mass matrix takes the Chebyshev
+    form with one kernel per iteration; FDAL_MASS_CHEB=0 keeps the Jacobi-PCG."""
     prob, H = P.get("stokes2d_exact")
     gpu = syn.setup_context(ALContext(prob.config), prob, H)
     assert gpu.mass_solver_info(0)["form"] == "dense"
-    assert gpu.mass_solver_info(1)["form"] == "cheb_persistent"
+    assert gpu.mass_solver_info(1)["form"] == "cheb_kernels"
     monkeypatch.setenv("FDAL_MASS_CHEB", "0")
     gpu0 = syn.setup_context(ALContext(prob.config), prob, H)
     assert gpu0.mass_solver_info(1)["form"] == "pcg_kernels"
@@ -63,16 +72,25 @@ def test_default_selection_and_off_switch(monkeypatch):
     PL.check("apply_mp_inv: Chebyshev vs Jacobi-PCG", P.relerr(gpu.apply_mp_inv(q)[0], gpu0.apply_mp_inv(q)[0]), 1e-13)
 
 
-def test_benched_elliptic_problem_at_full_size(oracle_mod):
-    """configs[2] as benched (cycle 6: 1 091 843 DoFs, multiplier space m = 20 609 > one CTA): default selection
-    is the persistent kernel; W^-1, the augmented operators and the block system against the oracle (SuperLU)."""
+@functools.lru_cache(maxsize=1)
+def _elliptic_cycle6():
     prob = syn.elliptic_interface(cycle=6)
-    H = syn.build_hierarchies(prob)
+    return prob, syn.build_hierarchies(prob)
+
+
+@pytest.mark.parametrize("form", ["default", "2"])
+def test_benched_elliptic_problem_at_full_size(form, oracle_mod, monkeypatch):
+    """configs[2] as benched (cycle 6: 1 091 843 DoFs, multiplier space m = 20 609): the default selection (one
+    fused kernel per Chebyshev iteration) and the persistent kernel; W^-1, the augmented operators and the block
+    system against the oracle (SuperLU)."""
+    if form != "default":
+        monkeypatch.setenv("FDAL_MASS_CHEB", form)
+    prob, H = _elliptic_cycle6()
     gpu = syn.setup_context(ALContext(prob.config), prob, H)
     ora = syn.setup_context(oracle_mod.OracleContext(prob.config), prob, H, oracle=True)
     info = gpu.mass_solver_info(0)
-    assert info["form"] == "cheb_persistent", (info, gpu.last_error())
-    PL.record("mass_cheb[elliptic_cycle6]", info)
+    assert info["form"] == ("cheb_kernels" if form == "default" else FORM[form]), (info, gpu.last_error())
+    PL.record(f"mass_cheb[elliptic_cycle6,{form}]", info)
     m = prob.sizes[-1]
     for seed in (1, 2):
         x = P.rand(m, seed)
