@@ -141,6 +141,8 @@ DEVICE_SIGNATURES = {
     "amg_set_replicated_from": (c_int, [c_void_p, c_int, c_int]),
     "comm_mode": (c_int, [c_void_p]),
     "mass_solver_info": (c_int, [c_void_p, c_int, _pi32, _pi32, _pd, _pd, _pd]),
+    "bsr_conversions": (c_int, [c_void_p, _pi32, _pi32]),
+    "csr_to_bsr": (c_int64, [c_int, c_int64, c_int64, _pi64, _pi32, _pd, c_int32, c_double, _pi32, c_int64, _pi32, _pd]),
     "assemble_al_term": (c_int, [c_int, c_int64, _pi64, _pi32, _pd, c_int64, c_int32, _pi32, _pd, _pd, _pi64]),
 }
 # only the oracle has these

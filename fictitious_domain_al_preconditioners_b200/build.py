@@ -14,8 +14,8 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB = os.path.join(CSRC, "libfdal.so")
-SOURCES = ["fdal.cu", "setup.cu"]
-HEADERS = ["kernels.cuh", "host_finalize.h", os.path.join("..", "..", "include", "fdal.h")]
+SOURCES = ["fdal.cu", "setup.cu", "bsr_build.cu"]
+HEADERS = ["kernels.cuh", "host_finalize.h", "bsr_build.h", os.path.join("..", "..", "include", "fdal.h")]
 
 
 def nvcc_path():

@@ -326,6 +326,12 @@ class ALContext:
         )
         return ms.value, by.value, nl.value
 
+    def bsr_conversions(self):
+        """(on_device, on_host): where the CSR -> BSR conversions of ``fdal_finalize`` ran (CUDA library only)."""
+        dev, host = C.c_int32(), C.c_int32()
+        self._check(self.api.bsr_conversions(self._h, C.byref(dev), C.byref(host)))
+        return dev.value, host.value
+
     MASS_FORMS = {0: "none", 1: "pcg_kernels", 2: "pcg_one_cta", 3: "dense", 4: "cheb_kernels", 5: "cheb_persistent"}
 
     def mass_solver_info(self, which: int = 0) -> dict:
@@ -337,6 +343,36 @@ class ALContext:
                                               C.byref(res)))
         return dict(form=self.MASS_FORMS.get(form.value, str(form.value)), iterations=its.value,
                     interval=(lo.value, hi.value), verified_residual=res.value)
+
+
+def csr_to_bsr(A, block_size: int, max_fill: float = 1.35, device: int = 0, api: b.Api | None = None):
+    """CSR -> BSR on the device (``fdal_csr_to_bsr``: the routine ``fdal_finalize`` uses for the dim-blocked
+    matrices).  Returns (brow_ptr, bcol, bval[nblk, b, b]) or None when the matrix is not blocked."""
+    import scipy.sparse as sp
+
+    if api is None:
+        from .lib import load
+
+        api = load()
+    A = sp.csr_matrix(A)
+    rp = np.ascontiguousarray(A.indptr, dtype=np.int64)
+    ci = np.ascontiguousarray(A.indices, dtype=np.int32)
+    v = np.ascontiguousarray(A.data, dtype=np.float64)
+    n = A.shape[0]
+    brp = np.zeros(n // block_size + 1, dtype=np.int32)
+    p64, p32 = C.POINTER(C.c_int64), C.POINTER(C.c_int32)
+    args = (device, n, A.nnz, rp.ctypes.data_as(p64), ci.ctypes.data_as(p32), b.dptr(v), block_size, max_fill,
+            brp.ctypes.data_as(p32))
+    nblk = api.csr_to_bsr(*args, 0, None, None)
+    if nblk == -1000:
+        return None
+    if nblk < 0:
+        raise FdalError(int(-nblk), "fdal_csr_to_bsr failed")
+    bcj = np.zeros(max(nblk, 1), dtype=np.int32)
+    bv = np.zeros(max(nblk, 1) * block_size * block_size, dtype=np.float64)
+    got = api.csr_to_bsr(*args, nblk, bcj.ctypes.data_as(p32), b.dptr(bv))
+    assert got == nblk
+    return brp, bcj[:nblk], bv[: nblk * block_size * block_size].reshape(nblk, block_size, block_size)
 
 
 def assemble_al_term(A, point_dofs, point_phi, weight, device: int = 0, api: b.Api | None = None):

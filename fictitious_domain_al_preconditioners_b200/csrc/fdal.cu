@@ -26,6 +26,7 @@
 #include <vector>
 
 #include "../../include/fdal.h"
+#include "bsr_build.h"
 #include "host_finalize.h"
 #include "kernels.cuh"
 
@@ -254,6 +255,7 @@ struct fdal_ctx {
   int spmv_unroll = 4;
   int bsr_unroll2 = 4, bsr_unroll3 = 1;  // blocks per lane in flight for 2x2 / 3x3 blocks (measured, profiles/)
   int fail = 0;
+  int bsr_built_on_device = 0, bsr_built_on_host = 0;  // CSR -> BSR conversions at fdal_finalize, by where they ran
   std::vector<void *> allocs;
   std::string err;
 };
@@ -312,23 +314,70 @@ static int choose_tpr(double avg) {
 
 // CSR -> BSR with B x B blocks (block-row SoA value layout, see k_bsr_spmv).  Returns false
 // (and leaves d untouched) when blocking would store too many explicit zeros.
+// FDAL_VERBOSE_SETUP: wall-clock of the phases of fdal_finalize on stderr
+struct PhaseTimer {
+  bool on = getenv("FDAL_VERBOSE_SETUP") != nullptr;
+  double t0 = omp_get_wtime();
+  void mark(const char *what, long long items = -1) {
+    if (!on) return;
+    const double t = omp_get_wtime();
+    if (items >= 0)
+      fprintf(stderr, "[fdal_finalize] %-44s %8.3f s  (%lld entries)\n", what, t - t0, items);
+    else
+      fprintf(stderr, "[fdal_finalize] %-44s %8.3f s\n", what, t - t0);
+    t0 = t;
+  }
+};
 static int build_bsr(fdal_ctx *c, const HostCsr &h, int b, DevCsr &d, bool *done) {
   *done = false;
-  IntBuf brp, bcj;
-  DblBuf bv;
-  if (!host_bsr_convert(h, b, 1.35, brp, bcj, bv)) return FDAL_OK;
+  if (b < 2 || b > 3 || h.nr % b || h.nc % b || h.owned_cols() % b || h.nr == 0) return FDAL_OK;
   const int64_t nbr = h.nr / b;
-  const int64_t nblk = brp[(size_t)nbr];
+  int64_t nblk = 0;
   int *drp = nullptr, *dcj = nullptr;
   double *dv = nullptr;
   int st;
-  if ((st = dmalloc(c, &drp, (size_t)nbr + 1))) return st;
-  if ((st = dmalloc(c, &dcj, (size_t)nblk))) return st;
-  if ((st = dmalloc(c, &dv, (size_t)nblk * b * b))) return st;
-  CU(cudaMemcpyAsync(drp, brp.data(), ((size_t)nbr + 1) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(dcj, bcj.data(), (size_t)nblk * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(dv, bv.data(), (size_t)nblk * b * b * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
+  bool on_device = false;
+  PhaseTimer pt;
+  // the scalar CSR arrays are on the device already (upload_csr): convert them there (csrc/bsr_build.cu).
+  // FDAL_HOST_BSR=1, or the device routine declining / failing, keeps the OpenMP conversion + a second upload.
+  const char *hb = getenv("FDAL_HOST_BSR");
+  const bool host_bsr = hb && atoi(hb) > 0;
+  if (!host_bsr && d.rp && d.ci && d.v) {
+    int max_entries = 0;
+#pragma omp parallel for schedule(static) reduction(max : max_entries)
+    for (int64_t I = 0; I < nbr; ++I)
+      max_entries = std::max(max_entries, h.rp[(size_t)((I + 1) * b)] - h.rp[(size_t)(I * b)]);
+    BsrBuilt built;
+    const int r = bsr_from_csr_device(c->stream, c->sms, (int)h.nr, h.nnz, d.rp, d.ci, d.v, b, max_entries, 1.35, &built);
+    if (r == BSR_BUILD_OK) {
+      drp = built.brp;
+      dcj = built.bcj;
+      dv = built.bv;
+      nblk = built.nblk;
+      c->allocs.push_back(drp);
+      c->allocs.push_back(dcj);
+      c->allocs.push_back(dv);
+      on_device = true;
+    } else if (r == BSR_BUILD_DECLINED) {
+      // zero fill too high / sizes: the host routine applies the same rules; fall through and let it decide
+    }
+  }
+  if (!on_device) {
+    IntBuf brp, bcj;
+    DblBuf bv;
+    if (!host_bsr_convert(h, b, 1.35, brp, bcj, bv)) return FDAL_OK;
+    nblk = brp[(size_t)nbr];
+    if ((st = dmalloc(c, &drp, (size_t)nbr + 1))) return st;
+    if ((st = dmalloc(c, &dcj, (size_t)nblk))) return st;
+    if ((st = dmalloc(c, &dv, (size_t)nblk * b * b))) return st;
+    CU(cudaMemcpyAsync(drp, brp.data(), ((size_t)nbr + 1) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(dcj, bcj.data(), (size_t)nblk * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(dv, bv.data(), (size_t)nblk * b * b * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  pt.mark(on_device ? "  CSR -> BSR on the device" : "  CSR -> BSR on the host + upload", h.nnz);
+  c->bsr_built_on_device += on_device ? 1 : 0;
+  c->bsr_built_on_host += on_device ? 0 : 1;
   d.bsr.nbrows = (int)nbr;
   d.bsr.rp = drp;
   d.bsr.cj = dcj;
@@ -2424,12 +2473,15 @@ int fdal_finalize(fdal_ctx *c) {
       c->chans.push_back(ch);
     }
   }
+  PhaseTimer pt;
   // explicit transposes (gather kernels only: no atomics, deterministic)
   if (!c->hmat[FDAL_MAT_C].set) host_transpose(c->hmat[FDAL_MAT_CT], c->hmat[FDAL_MAT_C]);
   if (is_stokes(c) && !c->hmat[FDAL_MAT_B].set) host_transpose(c->hmat[FDAL_MAT_BT], c->hmat[FDAL_MAT_B]);
+  pt.mark("transposes C = Ct^T, B = Bt^T (host)");
   for (int id = 0; id < FDAL_MAT_COUNT; ++id)
     if (c->hmat[id].set)
       if ((st = upload_csr(c, c->hmat[id], c->dmat[id], id == FDAL_MAT_A ? c->cfg.block_size : 1))) return st;
+  pt.mark("system matrices: upload (+ BSR of A)", c->hmat[FDAL_MAT_A].nnz);
   // Ct rides along in the row pass over A (fused augmented apply): flag the row chunks of A in which Ct
   // has any entry, so the other ~99 % of the chunks never look at Ct's row pointers
   {
@@ -2469,6 +2521,7 @@ int fdal_finalize(fdal_ctx *c) {
       if ((st = prepare_amg(c, c->amg[a], a == 0 && c->nranks > 1))) return st;
     }
   }
+  pt.mark("AMG hierarchies: upload (+ BSR of level 0)");
   // peer channels: everything that exchanges data has been registered by now
   if ((st = comm_build(c))) return st;
   // dots: the replicated tail blocks are counted on rank 0 only
@@ -2567,6 +2620,7 @@ int fdal_finalize(fdal_ctx *c) {
   if ((st = dvec(c, &c->d_y, mb + 8))) return st;
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaGetLastError());
+  pt.mark("workspaces, mass-solve calibration, Krylov bases");
   c->finalized = true;
   return FDAL_OK;
 }
@@ -2922,6 +2976,12 @@ int fdal_comm_init(fdal_ctx *c, const char id[128], int rank, int n_ranks) {
   return FDAL_OK;
 }
 int fdal_comm_mode(const fdal_ctx *c) { return c ? (c->nranks <= 1 ? 0 : (c->p2p ? 2 : 1)) : -1; }
+int fdal_bsr_conversions(const fdal_ctx *c, int32_t *on_device, int32_t *on_host) {
+  if (!c || !c->finalized) return FDAL_ERR_STATE;
+  if (on_device) *on_device = c->bsr_built_on_device;
+  if (on_host) *on_host = c->bsr_built_on_host;
+  return FDAL_OK;
+}
 int fdal_mass_solver_info(const fdal_ctx *c, int which, int32_t *form, int32_t *iterations, double *interval_lo,
                           double *interval_hi, double *verified_residual) {
   if (!c || !c->finalized || which < 0 || which > 1) return FDAL_ERR_STATE;

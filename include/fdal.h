@@ -324,6 +324,22 @@ enum {
 int fdal_mass_solver_info(const fdal_ctx *ctx, int which, int32_t *form, int32_t *iterations, double *interval_lo,
                           double *interval_hi, double *verified_residual);
 
+/* ---- setup phase on the device: CSR -> BSR conversion (part of SURVEY 8(f) N2: the data preparation the
+ * reference leaves to deal.II / Trilinos on the host) ---------------------------------------------------
+ * With fdal_config.block_size = 2 or 3 fdal_finalize stores the velocity / elasticity block and the finest AMG
+ * operator as BSR.  The conversion runs on the device on the scalar CSR arrays that were uploaded
+ * anyway (csrc/bsr_build.cu: per-warp shared-memory hash set of the block columns, prefix sum, sorted fill);
+ * FDAL_HOST_BSR=1 keeps the OpenMP conversion on the host.  fdal_bsr_conversions reports where the conversions of
+ * a finalized context ran.  fdal_csr_to_bsr is the same device routine with host arrays in and out (tests, tools):
+ * returns the number of blocks (>= 0), -1000 when the matrix is not blocked (explicit zeros > max_fill x nnz, or
+ * sizes beyond the 32-bit block pointers), or -FDAL_ERR_* .  brow_ptr_out has n_rows / block_size + 1 entries and is
+ * always written; bcol_out / bval_out (block_capacity blocks) are written when they are large enough, so a first
+ * call with block_capacity = 0 sizes the second.  Blocks are contiguous, row-major, block columns ascending. */
+int fdal_bsr_conversions(const fdal_ctx *ctx, int32_t *on_device, int32_t *on_host);
+int64_t fdal_csr_to_bsr(int device, int64_t n_rows, int64_t nnz, const int64_t *row_ptr, const int32_t *col,
+                        const double *val, int32_t block_size, double max_fill, int32_t *brow_ptr_out,
+                        int64_t block_capacity, int32_t *bcol_out, double *bval_out);
+
 /* ---- setup phase on the device -----------------------------------
  * Operator-form AL term (immersed_laplace.cc:659-702 with the particles of utilities.h:755-837;
  * nitsche_bcs.cc:517-572):  A += sum_q weight[q] * phi_q phi_q^T  scattered into the CSR values of the
