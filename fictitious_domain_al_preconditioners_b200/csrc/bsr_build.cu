@@ -18,6 +18,7 @@
 
 #include <limits.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #include <algorithm>
 #include <vector>
@@ -34,12 +35,13 @@ constexpr int kEmpty = -1;
 // insert J into the open-addressing set t[0, H); returns 1 when J was not there yet
 __device__ __forceinline__ int set_insert(int *t, int H, int logH, int J) {
   unsigned s = ((unsigned)J * 2654435761u) >> (32 - logH);
-  while (true) {
+  for (int probe = 0; probe < H; ++probe) {  // H >= 2 x the entries of the block row: never exhausted
     const int old = atomicCAS(&t[s], kEmpty, J);
     if (old == kEmpty) return 1;
     if (old == J) return 0;
     s = (s + 1) & (unsigned)(H - 1);
   }
+  return 0;
 }
 
 template <int B>
@@ -174,12 +176,14 @@ struct Scoped {  // frees on scope exit unless released
 
 }  // namespace
 
-#define BCU(call)                            \
-  do {                                       \
-    if ((call) != cudaSuccess) {             \
-      cudaGetLastError();                    \
-      return BSR_BUILD_CUDA_ERROR;           \
-    }                                        \
+#define BCU(call)                                                                                      \
+  do {                                                                                                 \
+    const cudaError_t e_ = (call);                                                                     \
+    if (e_ != cudaSuccess) {                                                                           \
+      fprintf(stderr, "fdal bsr_build: %s at %s:%d (%s)\n", cudaGetErrorString(e_), __FILE__, __LINE__, #call); \
+      cudaGetLastError();                                                                              \
+      return BSR_BUILD_CUDA_ERROR;                                                                     \
+    }                                                                                                  \
   } while (0)
 
 int bsr_from_csr_device(cudaStream_t stream, int sms, int nr, long long nnz, const int *rp, const int *ci, const double *v,
@@ -197,14 +201,18 @@ int bsr_from_csr_device(cudaStream_t stream, int sms, int nr, long long nnz, con
   int dev = 0, optin = 0;
   BCU(cudaGetDevice(&dev));
   BCU(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  if (H < 2 * max_row_entries || smem_fill > (size_t)optin) return BSR_BUILD_DECLINED;
-  if (b == 2) {
-    BCU(cudaFuncSetAttribute(k_bsr_count<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-    BCU(cudaFuncSetAttribute(k_bsr_fill<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-  } else {
-    BCU(cudaFuncSetAttribute(k_bsr_count<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-    BCU(cudaFuncSetAttribute(k_bsr_fill<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-  }
+  // dynamic shared memory above 48 KB is opt-in per kernel; the limit is the device maximum minus the kernel's
+  // static shared memory (k_bsr_fill keeps 16 bytes of it), so ask for exactly what the launch uses
+  const void *f_count = b == 2 ? (const void *)k_bsr_count<2> : (const void *)k_bsr_count<3>;
+  const void *f_fill = b == 2 ? (const void *)k_bsr_fill<2> : (const void *)k_bsr_fill<3>;
+  cudaFuncAttributes fa_count, fa_fill;
+  BCU(cudaFuncGetAttributes(&fa_count, f_count));
+  BCU(cudaFuncGetAttributes(&fa_fill, f_fill));
+  if (H < 2 * max_row_entries || smem_fill + fa_fill.sharedSizeBytes > (size_t)optin ||
+      smem_count + fa_count.sharedSizeBytes > (size_t)optin)
+    return BSR_BUILD_DECLINED;
+  if (smem_count > 48 * 1024) BCU(cudaFuncSetAttribute(f_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_count));
+  if (smem_fill > 48 * 1024) BCU(cudaFuncSetAttribute(f_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fill));
   Scoped<int> counts, brp, bcj;
   Scoped<long long> total;
   Scoped<double> bv;
