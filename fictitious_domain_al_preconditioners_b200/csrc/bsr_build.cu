@@ -28,7 +28,7 @@
 namespace fdal {
 namespace {
 
-constexpr int kWarps = 4;  // warps (= block rows in flight) per CTA
+constexpr int kWarps = 4;  // warps (= block rows in flight) per CTA; the host drops to 2 or 1 for very long block rows
 constexpr int kThreads = kWarps * 32;
 constexpr int kEmpty = -1;
 
@@ -48,9 +48,9 @@ template <int B>
 __global__ void __launch_bounds__(kThreads) k_bsr_count(int nbr, const int *__restrict__ rp, const int *__restrict__ ci,
                                                          int H, int logH, int *__restrict__ counts) {
   extern __shared__ int smem_i[];
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   int *t = smem_i + (size_t)w * H;
-  for (int I = blockIdx.x * kWarps + w; I < nbr; I += gridDim.x * kWarps) {
+  for (int I = blockIdx.x * nw + w; I < nbr; I += gridDim.x * nw) {
     for (int s = lane; s < H; s += 32) t[s] = kEmpty;
     __syncwarp();
     const int k0 = __ldg(rp + (size_t)I * B), k1 = __ldg(rp + (size_t)I * B + B);
@@ -105,10 +105,10 @@ __global__ void __launch_bounds__(kThreads) k_bsr_fill(int nbr, const int *__res
                                                         double *bv) {
   extern __shared__ int smem_i[];
   __shared__ int nlist[kWarps];
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   int *t = smem_i + (size_t)w * (H + H / 2);
   int *lst = t + H;  // [H / 2] >= distinct block columns of any block row (H >= 2 x its scalar entries)
-  for (int I = blockIdx.x * kWarps + w; I < nbr; I += gridDim.x * kWarps) {
+  for (int I = blockIdx.x * nw + w; I < nbr; I += gridDim.x * nw) {
     for (int s = lane; s < H; s += 32) t[s] = kEmpty;
     if (lane == 0) nlist[w] = 0;
     __syncwarp();
@@ -196,8 +196,8 @@ int bsr_from_csr_device(cudaStream_t stream, int sms, int nr, long long nnz, con
     H <<= 1;
     ++logH;
   }
-  const size_t smem_count = (size_t)kWarps * H * sizeof(int);
-  const size_t smem_fill = (size_t)kWarps * (H + H / 2) * sizeof(int);
+  int warps = kWarps;
+  size_t smem_count = 0, smem_fill = 0;
   int dev = 0, optin = 0;
   BCU(cudaGetDevice(&dev));
   BCU(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -208,9 +208,14 @@ int bsr_from_csr_device(cudaStream_t stream, int sms, int nr, long long nnz, con
   cudaFuncAttributes fa_count, fa_fill;
   BCU(cudaFuncGetAttributes(&fa_count, f_count));
   BCU(cudaFuncGetAttributes(&fa_fill, f_fill));
-  if (H < 2 * max_row_entries || smem_fill + fa_fill.sharedSizeBytes > (size_t)optin ||
-      smem_count + fa_count.sharedSizeBytes > (size_t)optin)
-    return BSR_BUILD_DECLINED;
+  if (H < 2 * max_row_entries) return BSR_BUILD_DECLINED;
+  for (;; warps >>= 1) {  // fewer block rows in flight per CTA when one block row's set is large
+    smem_count = (size_t)warps * H * sizeof(int);
+    smem_fill = (size_t)warps * (H + H / 2) * sizeof(int);
+    if (smem_fill + fa_fill.sharedSizeBytes <= (size_t)optin && smem_count + fa_count.sharedSizeBytes <= (size_t)optin) break;
+    if (warps == 1) return BSR_BUILD_DECLINED;
+  }
+  const int threads = warps * 32;
   if (smem_count > 48 * 1024) BCU(cudaFuncSetAttribute(f_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_count));
   if (smem_fill > 48 * 1024) BCU(cudaFuncSetAttribute(f_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fill));
   Scoped<int> counts, brp, bcj;
@@ -222,13 +227,13 @@ int bsr_from_csr_device(cudaStream_t stream, int sms, int nr, long long nnz, con
   // grid: every SM full of CTAs (shared memory is the limit), grid-stride over the block rows
   const int per_sm_count = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)optin / std::max<size_t>(smem_count, 1)));
   const int per_sm_fill = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)optin / std::max<size_t>(smem_fill, 1)));
-  const int need = (nbr + kWarps - 1) / kWarps;
+  const int need = (nbr + warps - 1) / warps;
   const int g_count = std::max(1, std::min(need, sms * per_sm_count));
   const int g_fill = std::max(1, std::min(need, sms * per_sm_fill));
   if (b == 2)
-    k_bsr_count<2><<<g_count, kThreads, smem_count, stream>>>(nbr, rp, ci, H, logH, counts.p);
+    k_bsr_count<2><<<g_count, threads, smem_count, stream>>>(nbr, rp, ci, H, logH, counts.p);
   else
-    k_bsr_count<3><<<g_count, kThreads, smem_count, stream>>>(nbr, rp, ci, H, logH, counts.p);
+    k_bsr_count<3><<<g_count, threads, smem_count, stream>>>(nbr, rp, ci, H, logH, counts.p);
   BCU(cudaGetLastError());
   k_scan_counts<<<1, 1024, 0, stream>>>(nbr, counts.p, brp.p, total.p);
   BCU(cudaGetLastError());
@@ -241,9 +246,9 @@ int bsr_from_csr_device(cudaStream_t stream, int sms, int nr, long long nnz, con
   BCU(cudaMalloc((void **)&bv.p, (size_t)nblk * b * b * sizeof(double)));
   BCU(cudaMemsetAsync(bv.p, 0, (size_t)nblk * b * b * sizeof(double), stream));
   if (b == 2)
-    k_bsr_fill<2><<<g_fill, kThreads, smem_fill, stream>>>(nbr, rp, ci, v, H, logH, brp.p, bcj.p, bv.p);
+    k_bsr_fill<2><<<g_fill, threads, smem_fill, stream>>>(nbr, rp, ci, v, H, logH, brp.p, bcj.p, bv.p);
   else
-    k_bsr_fill<3><<<g_fill, kThreads, smem_fill, stream>>>(nbr, rp, ci, v, H, logH, brp.p, bcj.p, bv.p);
+    k_bsr_fill<3><<<g_fill, threads, smem_fill, stream>>>(nbr, rp, ci, v, H, logH, brp.p, bcj.p, bv.p);
   BCU(cudaGetLastError());
   BCU(cudaStreamSynchronize(stream));
   out->brp = brp.release();

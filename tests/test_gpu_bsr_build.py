@@ -62,7 +62,8 @@ def test_device_conversion_equals_host_conversion(b, nb, density):
 
 
 def test_long_block_rows_and_empty_block_rows():
-    """One block row with thousands of entries (the hash set is sized by the longest block row), many empty ones."""
+    """One block row with 7 800 scalar entries (the hash set is sized by the longest block row: 16 384 slots, two
+    block rows in flight per CTA instead of four), many empty ones."""
     b, nb = 3, 1500
     rng = np.random.default_rng(1)
     A = sp.lil_matrix((nb * b, nb * b))
@@ -77,6 +78,20 @@ def test_long_block_rows_and_empty_block_rows():
     for d, h in zip(dev, host):
         assert np.array_equal(d, h)
     assert np.all(np.diff(dev[0])[1:7] == 0)  # empty block rows
+
+
+def test_block_rows_beyond_the_shared_memory_set_are_left_to_the_host():
+    """27 000 scalar entries in one block row would need a 65 536-slot set (393 KB for one warp): the device routine
+    declines, the host conversion (the fallback inside fdal_finalize) still blocks the matrix."""
+    b, nb = 3, 4000
+    rng = np.random.default_rng(2)
+    A = sp.lil_matrix((nb * b, nb * b))
+    cols = rng.choice(nb * b, 9000, replace=False)
+    for r in range(b):
+        A[5 * b + r, cols] = 1.0
+    A = sp.csr_matrix(A + sp.identity(nb * b))
+    assert csr_to_bsr(A, b, max_fill=100.0) is None
+    assert _host_bsr(A, b, max_fill=100.0) is not None
 
 
 def test_device_conversion_declines_like_the_host():

@@ -150,3 +150,21 @@ def test_reference_classes_on_the_cuda_library(name, oracle_mod):
     xa, infa, st = ac.solve(lib, gpu, rhs)
     x, info = gpu.solve(rhs)
     assert st == 0 and infa.outer_iterations == info.outer_iterations and np.array_equal(xa, x)
+
+
+# ---- "Do parameter study" of elliptic_interface (elliptic_interface.cc:1086-1128): one solve per sampled gamma,
+# the first value with the fewest outer iterations wins; CUDA library and oracle must pick the same value
+def test_gamma_parameter_study_matches_the_oracle(oracle_mod):
+    from fictitious_domain_al_preconditioners_b200 import parameter_study as ps
+    from fictitious_domain_al_preconditioners_b200 import synthetic as syn
+
+    gammas = ps.linspace(1e-3, 10.0, 4)
+    make = lambda g: syn.elliptic_interface(cycle=1, gamma_fluid=g, gamma_solid=g)  # noqa: E731
+    hier = lambda p: syn.build_hierarchies(p, max_coarse=300)  # noqa: E731
+    gpu = ps.gamma_parameter_study(make, gammas, build_hierarchies=hier)
+    ora = ps.gamma_parameter_study(make, gammas, make_context=lambda cfg: oracle_mod.OracleContext(cfg), build_hierarchies=hier)
+    PL.record("gamma_parameter_study", {"gammas": gammas, "outer_gpu": gpu.outer_iterations, "outer_oracle": ora.outer_iterations})
+    assert all(abs(a - b) <= 1 for a, b in zip(gpu.outer_iterations, ora.outer_iterations))
+    # the chosen gamma agrees unless two samples tie within the +/-1 band of the outer counts
+    if gpu.best_gamma != ora.best_gamma:
+        assert abs(min(gpu.outer_iterations) - ora.outer_iterations[gpu.min_index]) <= 1
