@@ -22,6 +22,9 @@
  *     val[nnz]; entries within a row may come in any order (deal.II stores the
  *     diagonal first, reference SURVEY A.7) — the library keeps the order it
  *     is given, so floating-point summation order is the caller's order.
+ *     Exception: with fdal_config.block_size > 1 the matrix A and the finest
+ *     AMG operator are stored as BSR with the block columns of a block row
+ *     sorted ascending, so their row sums run in block-column order.
  *   - host-pointer calls copy their arguments; the caller's arrays only need
  *     to live for the duration of the call.
  *   - block vectors are passed as ONE contiguous array [block0|block1|block2]
