@@ -1029,9 +1029,6 @@ static void mass_solve_fixed(fdal_ctx *c, CgWs &w, const DevCsr &M, const double
   if (!done) whole();
   dcopy(c, w.n, w.x, x);
 }
-struct CgHistory {
-  std::vector<double> rho, pv;  // r.z and p.Ap of every iteration
-};
 static int mass_calibrate(fdal_ctx *c, CgWs &w, const DevCsr &M, const double *invdiag, int *its_out,
                           CgHistory *lanczos = nullptr) {
   // count the iterations Jacobi-PCG needs to push the recursive residual below
@@ -1076,60 +1073,7 @@ static int mass_calibrate(fdal_ctx *c, CgWs &w, const DevCsr &M, const double *i
   return FDAL_OK;
 }
 
-// ---- Chebyshev form of the exact mass solves ----------------------------------------------------
-// extreme eigenvalues of the symmetric tridiagonal matrix (d, e) by Sturm bisection
-static void tridiag_extremes(const std::vector<double> &d, const std::vector<double> &e, double *lo_out, double *hi_out) {
-  const int n = (int)d.size();
-  double gl = d[0], gu = d[0];
-  for (int i = 0; i < n; ++i) {
-    const double r = (i > 0 ? std::fabs(e[(size_t)i - 1]) : 0.0) + (i + 1 < n ? std::fabs(e[(size_t)i]) : 0.0);
-    gl = std::min(gl, d[(size_t)i] - r);
-    gu = std::max(gu, d[(size_t)i] + r);
-  }
-  auto count_below = [&](double x) {  // eigenvalues < x
-    int cnt = 0;
-    double q = d[0] - x;
-    for (int i = 0;; ++i) {
-      if (q < 0.0) ++cnt;
-      if (i + 1 == n) break;
-      if (q == 0.0) q = 1e-300;
-      q = d[(size_t)i + 1] - x - e[(size_t)i] * e[(size_t)i] / q;
-    }
-    return cnt;
-  };
-  auto kth = [&](int k) {  // smallest x with count_below(x) >= k, i.e. the k-th eigenvalue (1-based)
-    double a = gl, b = gu;
-    for (int i = 0; i < 200 && b - a > 1e-15 * std::max(std::fabs(a), std::fabs(b)); ++i) {
-      const double mid = 0.5 * (a + b);
-      if (count_below(mid) >= k)
-        b = mid;
-      else
-        a = mid;
-    }
-    return 0.5 * (a + b);
-  };
-  *lo_out = kth(1);
-  *hi_out = kth(n);
-}
-// Ritz values of D^-1 M from the CG coefficients of the calibration solve (Lanczos connection:
-// T_jj = 1/alpha_j + beta_j/alpha_{j-1}, T_{j,j+1} = sqrt(beta_{j+1})/alpha_j)
-static bool lanczos_bounds(const CgHistory &h, double *lo, double *hi) {
-  std::vector<double> d, e;
-  double alpha_prev = 0.0;
-  for (size_t j = 0; j < h.rho.size(); ++j) {
-    const double rho = h.rho[j], pv = h.pv[j];
-    if (!(rho > 0.0) || !(pv > 0.0) || !std::isfinite(rho) || !std::isfinite(pv)) break;
-    const double alpha = rho / pv;
-    const double beta = j > 0 ? rho / h.rho[j - 1] : 0.0;
-    if (j > 0) e.push_back(std::sqrt(beta) / alpha_prev);
-    d.push_back(1.0 / alpha + (j > 0 ? beta / alpha_prev : 0.0));
-    alpha_prev = alpha;
-  }
-  if (d.size() < 3) return false;
-  e.resize(d.size() - 1);
-  tridiag_extremes(d, e, lo, hi);
-  return *lo > 0.0 && *hi > *lo && std::isfinite(*hi);
-}
+// ---- Chebyshev form of the exact mass solves (bounds and coefficients: csrc/host_finalize.h) ------
 static void mass_cheb_kernels(fdal_ctx *c, MassCheb &mc, CgWs &w, const DevCsr &M, const double *invdiag,
                               const double *b, double *x) {
   // iterate ping-pongs between w.x and w.v, d lives in w.p; the last step writes x
@@ -1187,27 +1131,9 @@ static int mass_cheb_setup(fdal_ctx *c, MassCheb &mc, CgWs &w, const DevCsr &M, 
   const int want = env ? atoi(env) : 1;
   mc.mode = 0;
   if (want <= 0 || w.dist || w.n < 2 || M.use_bsr) return FDAL_OK;
-  double lo, hi;
-  if (!lanczos_bounds(h, &lo, &hi)) return FDAL_OK;
-  // Ritz values lie inside the spectrum: widen by 3 % on either side (costs ~2 iterations)
-  mc.lo = 0.97 * lo;
-  mc.hi = 1.03 * hi;
-  const double theta = 0.5 * (mc.hi + mc.lo), delta = 0.5 * (mc.hi - mc.lo), s1 = theta / delta;
-  const double sk = std::sqrt(mc.hi / mc.lo), q = (sk - 1.0) / (sk + 1.0);
   const int cap = c->cfg.exact_mass_max_its > 0 ? c->cfg.exact_mass_max_its : 300;
-  int its = (int)std::ceil(std::log(2.0e16) / -std::log(q)) + 2;  // 2 q^k / (1 + q^2k) <= 1e-16
-  if (its > cap) return FDAL_OK;
-  its = std::max(its, 2);
-  mc.its = its;
-  mc.coef.assign(2 * (size_t)its, 0.0);
-  mc.coef[1] = 1.0 / theta;
-  double rho = 1.0 / s1;
-  for (int k = 1; k < its; ++k) {
-    const double rho1 = 1.0 / (2.0 * s1 - rho);
-    mc.coef[2 * (size_t)k] = rho1 * rho;
-    mc.coef[2 * (size_t)k + 1] = 2.0 * rho1 / delta;
-    rho = rho1;
-  }
+  if (!chebyshev_plan(h, cap, &mc.lo, &mc.hi, &mc.its, mc.coef)) return FDAL_OK;
+  const int its = mc.its;
   int st;
   int mode = 1;
   if (want >= 2 && M.d.nnz < (1ll << 31)) {

@@ -1,12 +1,14 @@
 // host_finalize.h — the host-side (OpenMP) data preparation of fdal_finalize: CSR copies without a
 // value-initialising pass, the stable transpose (C = Ct^T, B = Bt^T, R = P^T: SparseMatrix::Tvmult of the
-// reference becomes a gather) and the CSR -> BSR conversion of the dim-blocked matrices.  No CUDA in here, so
+// reference becomes a gather), the CSR -> BSR conversion of the dim-blocked matrices (fallback of the device
+// conversion) and the plan of the Chebyshev mass solves (Lanczos bounds, iteration count, coefficients).  No CUDA in here, so
 // the same code is compiled into csrc/libfdal_host.so for the CPU tests (tests/test_host_finalize.py).
 #pragma once
 #include <omp.h>
 #include <stdint.h>
 
 #include <algorithm>
+#include <cmath>
 #include <limits>
 #include <memory>
 #include <utility>
@@ -158,6 +160,94 @@ inline bool host_bsr_convert(const HostCsr &h, int b, double max_fill, IntBuf &b
         }
     }
   }
+  return true;
+}
+
+// ---- exact mass inverses in Chebyshev form: everything that is decided on the host ------------------------
+struct CgHistory {
+  std::vector<double> rho, pv;  // r.z and p.Ap of every iteration of the calibration CG
+};
+// extreme eigenvalues of the symmetric tridiagonal matrix (d, e) by Sturm bisection
+inline void tridiag_extremes(const std::vector<double> &d, const std::vector<double> &e, double *lo_out, double *hi_out) {
+  const int n = (int)d.size();
+  double gl = d[0], gu = d[0];
+  for (int i = 0; i < n; ++i) {
+    const double r = (i > 0 ? std::fabs(e[(size_t)i - 1]) : 0.0) + (i + 1 < n ? std::fabs(e[(size_t)i]) : 0.0);
+    gl = std::min(gl, d[(size_t)i] - r);
+    gu = std::max(gu, d[(size_t)i] + r);
+  }
+  auto count_below = [&](double x) {  // eigenvalues < x
+    int cnt = 0;
+    double q = d[0] - x;
+    for (int i = 0;; ++i) {
+      if (q < 0.0) ++cnt;
+      if (i + 1 == n) break;
+      if (q == 0.0) q = 1e-300;
+      q = d[(size_t)i + 1] - x - e[(size_t)i] * e[(size_t)i] / q;
+    }
+    return cnt;
+  };
+  auto kth = [&](int k) {  // smallest x with count_below(x) >= k, i.e. the k-th eigenvalue (1-based)
+    double a = gl, b = gu;
+    for (int i = 0; i < 200 && b - a > 1e-15 * std::max(std::fabs(a), std::fabs(b)); ++i) {
+      const double mid = 0.5 * (a + b);
+      if (count_below(mid) >= k)
+        b = mid;
+      else
+        a = mid;
+    }
+    return 0.5 * (a + b);
+  };
+  *lo_out = kth(1);
+  *hi_out = kth(n);
+}
+// Ritz values of D^-1 M from the CG coefficients of the calibration solve (Lanczos connection:
+// T_jj = 1/alpha_j + beta_j/alpha_{j-1}, T_{j,j+1} = sqrt(beta_{j+1})/alpha_j)
+inline bool lanczos_bounds(const CgHistory &h, double *lo, double *hi) {
+  std::vector<double> d, e;
+  double alpha_prev = 0.0;
+  for (size_t j = 0; j < h.rho.size() && j < h.pv.size(); ++j) {
+    const double rho = h.rho[j], pv = h.pv[j];
+    if (!(rho > 0.0) || !(pv > 0.0) || !std::isfinite(rho) || !std::isfinite(pv)) break;
+    const double alpha = rho / pv;
+    const double beta = j > 0 ? rho / h.rho[j - 1] : 0.0;
+    if (j > 0) e.push_back(std::sqrt(beta) / alpha_prev);
+    d.push_back(1.0 / alpha + (j > 0 ? beta / alpha_prev : 0.0));
+    alpha_prev = alpha;
+  }
+  if (d.size() < 3) return false;
+  e.resize(d.size() - 1);
+  tridiag_extremes(d, e, lo, hi);
+  return *lo > 0.0 && *hi > *lo && std::isfinite(*hi);
+}
+// The fixed-count Chebyshev iteration on D^-1 M that replaces the exact mass solve: spectral interval = the Ritz
+// interval widened by 3 % on either side (Ritz values lie inside the spectrum; costs ~2 iterations), iteration
+// count from the Chebyshev error bound 2 q^k / (1 + q^2k) <= 1e-16 (+2), coefficients of
+//   r = b - M x ; d = c1_k d + c2_k D^-1 r ; x += d        (coef[2k] = c1_k, coef[2k+1] = c2_k, c1_0 = 0).
+// Returns false (keep the Jacobi-PCG) when the bounds are unusable or the count exceeds `cap`.
+inline bool chebyshev_plan(const CgHistory &h, int cap, double *lo_out, double *hi_out, int *its_out,
+                           std::vector<double> &coef) {
+  double lo, hi;
+  if (!lanczos_bounds(h, &lo, &hi)) return false;
+  lo *= 0.97;
+  hi *= 1.03;
+  const double theta = 0.5 * (hi + lo), delta = 0.5 * (hi - lo), s1 = theta / delta;
+  const double sk = std::sqrt(hi / lo), q = (sk - 1.0) / (sk + 1.0);
+  int its = (int)std::ceil(std::log(2.0e16) / -std::log(q)) + 2;
+  if (its > cap) return false;
+  its = std::max(its, 2);
+  coef.assign(2 * (size_t)its, 0.0);
+  coef[1] = 1.0 / theta;
+  double rho = 1.0 / s1;
+  for (int k = 1; k < its; ++k) {
+    const double rho1 = 1.0 / (2.0 * s1 - rho);
+    coef[2 * (size_t)k] = rho1 * rho;
+    coef[2 * (size_t)k + 1] = 2.0 * rho1 / delta;
+    rho = rho1;
+  }
+  *lo_out = lo;
+  *hi_out = hi;
+  *its_out = its;
   return true;
 }
 

@@ -36,4 +36,18 @@ int64_t fdal_hostfin_bsr(int64_t nr, int64_t nc, int64_t nnz, const int64_t *rp,
   return (int64_t)cj_.size();
 }
 
+// Chebyshev plan of an exact mass solve from the (r.z, p.Ap) history of a Jacobi-PCG run.  Returns the iteration
+// count (0: no plan); coef_out must hold 2 * cap doubles.
+int32_t fdal_hostfin_cheb_plan(int32_t n_hist, const double *rho, const double *pv, int32_t cap, double *lo, double *hi,
+                               double *coef_out) {
+  CgHistory h;
+  h.rho.assign(rho, rho + n_hist);
+  h.pv.assign(pv, pv + n_hist);
+  std::vector<double> coef;
+  int its = 0;
+  if (!chebyshev_plan(h, cap, lo, hi, &its, coef)) return 0;
+  std::memcpy(coef_out, coef.data(), coef.size() * sizeof(double));
+  return its;
+}
+
 }  // extern "C"

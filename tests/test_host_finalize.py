@@ -134,3 +134,58 @@ def test_bsr_conversion_declines(lib):
     rp, ci, v = _ptrs(B)
     assert lib.fdal_hostfin_bsr(13, 13, B.nnz, _p(rp, C.c_int64), _p(ci, C.c_int32), _p(v, C.c_double), 3, 10.0,
                                 _p(brp, C.c_int32), None, None) == -1
+
+
+def test_chebyshev_plan_of_the_exact_mass_solve(lib):
+    """The host half of the Chebyshev mass solve (csrc/host_finalize.h: Lanczos bounds from the calibration CG,
+    iteration count, coefficients) on the immersed mass matrix of elliptic_interface: the Ritz interval lies inside
+    the spectrum of D^-1 M and is tight, and the fixed-count recurrence with the returned coefficients solves
+    M x = b to rounding."""
+    import scipy.sparse.linalg as sla
+
+    from fictitious_domain_al_preconditioners_b200 import synthetic as syn
+
+    M = syn.elliptic_interface(cycle=3).M.tocsr()
+    n = M.shape[0]
+    invd = 1.0 / M.diagonal()
+    b = np.random.default_rng(0).uniform(-1, 1, n)
+    # Jacobi-PCG as mass_calibrate runs it: record r.z and p.Ap
+    x, r, p, rho_old = np.zeros(n), b.copy(), np.zeros(n), np.inf
+    rhos, pvs, rr0 = [], [], b @ b
+    while np.sqrt(r @ r) > 1e-17 * np.sqrt(rr0) and len(rhos) < 300:
+        z = invd * r
+        rho = r @ z
+        p = z + (0.0 if np.isinf(rho_old) else rho / rho_old) * p
+        v = M @ p
+        pv = p @ v
+        x += rho / pv * p
+        r -= rho / pv * v
+        rho_old = rho
+        rhos.append(rho)
+        pvs.append(pv)
+    rho_a, pv_a = np.array(rhos), np.array(pvs)
+    lib.fdal_hostfin_cheb_plan.restype = C.c_int32
+    lib.fdal_hostfin_cheb_plan.argtypes = [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int32,
+                                           C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lo, hi = C.c_double(), C.c_double()
+    coef = np.zeros(600)
+    its = lib.fdal_hostfin_cheb_plan(len(rhos), _p(rho_a, C.c_double), _p(pv_a, C.c_double), 300, C.byref(lo), C.byref(hi),
+                                     _p(coef, C.c_double))
+    Dh = sp.diags(np.sqrt(invd))
+    ev = np.linalg.eigvalsh((Dh @ M @ Dh).toarray())
+    assert lo.value <= ev[0] * 1.001 and hi.value >= ev[-1] * 0.999  # widened Ritz interval covers the spectrum
+    assert lo.value >= 0.9 * ev[0] and hi.value <= 1.1 * ev[-1]      # and is tight
+    assert 30 <= its <= 80 and coef[0] == 0.0
+    d = coef[1] * invd * b
+    y = d.copy()
+    for k in range(1, its):
+        d = coef[2 * k] * d + coef[2 * k + 1] * invd * (b - M @ y)
+        y = y + d
+    assert np.linalg.norm(b - M @ y) <= 2e-15 * np.linalg.norm(b)
+    assert np.linalg.norm(y - sla.spsolve(M.tocsc(), b)) <= 1e-14 * np.linalg.norm(y)
+    # an unusable history (too short / non-positive) gives no plan
+    assert lib.fdal_hostfin_cheb_plan(2, _p(rho_a, C.c_double), _p(pv_a, C.c_double), 300, C.byref(lo), C.byref(hi),
+                                      _p(coef, C.c_double)) == 0
+    # and so does a cap below the needed count
+    assert lib.fdal_hostfin_cheb_plan(len(rhos), _p(rho_a, C.c_double), _p(pv_a, C.c_double), 10, C.byref(lo), C.byref(hi),
+                                      _p(coef, C.c_double)) == 0
