@@ -101,3 +101,35 @@ def test_dealii_example_compiles():
                     "-I", os.path.join(stub, "dealii_stub"), "-I", os.path.join(stub, "trilinos_stub"),
                     "-I", os.path.join(ROOT, "include"), "-DFDAL_STUB_TRILINOS",
                     os.path.join(ROOT, "examples", "dealii_immersed_laplace_solve.cc")], check=True)
+
+
+def test_stand_alone_setup_entry_points_validate_before_touching_a_device():
+    """fdal_assemble_al_term / fdal_csr_to_bsr (no context): bad arguments are refused with FDAL_ERR_INVALID /
+    FDAL_ERR_SHAPE, and without a CUDA device the calls fail loudly with FDAL_ERR_CUDA (no CPU fallback)."""
+    import numpy as np
+    import torch
+
+    api = lib.load()
+    p64, p32, pd = ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_double)
+    rp = np.array([0, 1, 2, 3, 4, 5, 6], dtype=np.int64)
+    ci = np.arange(6, dtype=np.int32)
+    v = np.ones(6)
+    brp = np.zeros(4, dtype=np.int32)
+    a = (rp.ctypes.data_as(p64), ci.ctypes.data_as(p32), v.ctypes.data_as(pd))
+    # block size out of range / rows not a multiple of it / null arrays
+    assert api.csr_to_bsr(0, 6, 6, *a, 4, 1.35, brp.ctypes.data_as(p32), 0, None, None) == -b.ERR_INVALID
+    assert api.csr_to_bsr(0, 5, 5, *a, 2, 1.35, brp.ctypes.data_as(p32), 0, None, None) == -b.ERR_INVALID
+    assert api.csr_to_bsr(0, 6, 6, None, a[1], a[2], 2, 1.35, brp.ctypes.data_as(p32), 0, None, None) == -b.ERR_INVALID
+    dofs = np.array([[0, 7]], dtype=np.int32)  # dof 7 >= n_rows = 6
+    phi = np.array([[0.5, 0.5]])
+    w = np.ones(1)
+    miss = ctypes.c_int64(0)
+    al = lambda n_pts, dpc, d: api.assemble_al_term(0, 6, a[0], a[1], a[2], n_pts, dpc, d.ctypes.data_as(p32),  # noqa: E731
+                                                      phi.ctypes.data_as(pd), w.ctypes.data_as(pd), ctypes.byref(miss))
+    assert al(1, 2, dofs) == b.ERR_SHAPE
+    assert al(1, 0, dofs) == b.ERR_INVALID
+    assert al(-1, 2, dofs) == b.ERR_INVALID
+    if not torch.cuda.is_available():
+        ok = np.array([[0, 1]], dtype=np.int32)
+        assert al(1, 2, ok) == b.ERR_CUDA
+        assert api.csr_to_bsr(0, 6, 6, *a, 2, 1.35, brp.ctypes.data_as(p32), 0, None, None) == -b.ERR_CUDA
